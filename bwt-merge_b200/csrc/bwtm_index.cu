@@ -1,0 +1,605 @@
+// K0: device rank structure from run-length bytes, and the batched query entry points.
+//
+// Replaces BWT::build (bwt.cpp:476-512): the reference scans the run bytes once and stores, per
+// 64-byte block, the last sequence position and six cumulative counts in seven sparse bitvectors.
+// Here the run bytes are decoded once into position-addressed 64-byte records (bwtm_common.cuh).
+#include <atomic>
+#include <cstdarg>
+#include <cstring>
+#include <mutex>
+#include <string>
+
+#include <cub/cub.cuh>
+
+#include "bwtm_internal.cuh"
+
+namespace bwtm
+{
+
+//------------------------------------------------------------------------------
+// Errors, launch counter
+
+static thread_local std::string last_error_message;
+static std::atomic<uint64_t>* launch_counter()
+{
+  static std::atomic<uint64_t> counter(0);
+  return &counter;
+}
+
+void set_error(const char* fmt, ...)
+{
+  char buffer[1024];
+  va_list args; va_start(args, fmt);
+  vsnprintf(buffer, sizeof(buffer), fmt, args);
+  va_end(args);
+  last_error_message = buffer;
+}
+
+int cuda_failed(cudaError_t err, const char* what, const char* file, int line)
+{
+  set_error("CUDA error %d (%s) in %s at %s:%d", (int)err, cudaGetErrorString(err), what, file, line);
+  return (err == cudaErrorMemoryAllocation ? BWTM_ERR_MEMORY : BWTM_ERR_CUDA);
+}
+
+void count_launch(uint64_t n) { launch_counter()->fetch_add(n); }
+
+int DeviceBuffer::allocate(uint64_t n)
+{
+  this->release();
+  if(n == 0) { n = 16; }
+  cudaError_t err = cudaMalloc(&(this->ptr), n);
+  if(err != cudaSuccess)
+  {
+    this->ptr = nullptr;
+    set_error("cudaMalloc of %llu bytes failed: %s", (unsigned long long)n, cudaGetErrorString(err));
+    cudaGetLastError();
+    return BWTM_ERR_MEMORY;
+  }
+  this->bytes = n;
+  return BWTM_OK;
+}
+
+void DeviceBuffer::release()
+{
+  if(this->ptr != nullptr) { cudaFree(this->ptr); this->ptr = nullptr; this->bytes = 0; }
+}
+
+//------------------------------------------------------------------------------
+// Run decoding of one 64-byte block held in shared memory (Run::read, support.h:244-250;
+// ByteCode::read, support.h:172-184). `limit` is the number of valid bytes in the block.
+
+constexpr int K0_THREADS = 128;
+constexpr int K0_STRIDE  = 68;   // bytes per staged block: 17 words, so that lanes hit distinct banks
+
+template<class Visitor>
+__device__ __forceinline__ void decode_staged_block(const uint8_t* block, int limit, Visitor&& visit)
+{
+  int pos = 0;
+  while(pos < limit)
+  {
+    uint32_t code = block[pos++];
+    uint32_t comp = code % SIGMA;
+    uint64_t length = code / SIGMA + 1;
+    if(length >= MAX_RUN)
+    {
+      int shift = 0;
+      while(pos < limit)
+      {
+        uint32_t b = block[pos++];
+        if(shift < 64) { length += (uint64_t)(b & 0x7Fu) << shift; }
+        shift += 7;
+        if(!(b & 0x80u)) { break; }
+      }
+    }
+    visit(comp, length);
+  }
+}
+
+// Coalesced copy of K0_THREADS consecutive 64-byte blocks into padded shared memory.
+__device__ __forceinline__ void stage_blocks(const uint8_t* rle, uint64_t first_block, uint64_t rle_bytes, uint8_t* smem)
+{
+  // The rle buffer is padded with zeros to a multiple of 16 beyond rle_bytes, so 16-byte loads are safe.
+  const uint4* src = reinterpret_cast<const uint4*>(rle + first_block * RLE_BLOCK);
+  uint64_t total_vec = div_up(rle_bytes, 16);
+  uint64_t base_vec = first_block * (RLE_BLOCK / 16);
+  for(int v = threadIdx.x; v < K0_THREADS * (RLE_BLOCK / 16); v += K0_THREADS)
+  {
+    uint4 value = make_uint4(0, 0, 0, 0);
+    if(base_vec + v < total_vec) { value = src[v]; }
+    int block = v >> 2, part = v & 3;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(smem + block * K0_STRIDE + part * 16);
+    dst[0] = value.x; dst[1] = value.y; dst[2] = value.z; dst[3] = value.w;
+  }
+}
+
+__global__ void __launch_bounds__(K0_THREADS)
+k0_block_lengths(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t blocks, uint64_t* __restrict__ lengths)
+{
+  __shared__ __align__(16) uint8_t smem[K0_THREADS * K0_STRIDE];
+  uint64_t first_block = (uint64_t)blockIdx.x * K0_THREADS;
+  stage_blocks(rle, first_block, rle_bytes, smem);
+  __syncthreads();
+
+  uint64_t block = first_block + threadIdx.x;
+  if(block >= blocks) { return; }
+  uint64_t begin = block * RLE_BLOCK;
+  int limit = (int)(rle_bytes - begin < (uint64_t)RLE_BLOCK ? rle_bytes - begin : (uint64_t)RLE_BLOCK);
+  uint64_t total = 0;
+  decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t, uint64_t length) { total += length; });
+  lengths[block] = total;
+}
+
+// Sets the plane bits of every run. Records must be zero-initialised.
+__global__ void __launch_bounds__(K0_THREADS)
+k0_fill_planes(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t blocks,
+               const uint64_t* __restrict__ starts, uint32_t* __restrict__ record_words)
+{
+  __shared__ __align__(16) uint8_t smem[K0_THREADS * K0_STRIDE];
+  uint64_t first_block = (uint64_t)blockIdx.x * K0_THREADS;
+  stage_blocks(rle, first_block, rle_bytes, smem);
+  __syncthreads();
+
+  uint64_t block = first_block + threadIdx.x;
+  if(block >= blocks) { return; }
+  uint64_t begin = block * RLE_BLOCK;
+  int limit = (int)(rle_bytes - begin < (uint64_t)RLE_BLOCK ? rle_bytes - begin : (uint64_t)RLE_BLOCK);
+  uint64_t pos = starts[block];
+  decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
+  {
+    if(comp != 0)
+    {
+      uint64_t p = pos, remaining = length;
+      while(remaining > 0)
+      {
+        uint64_t group = p >> 5;            // 32-position chunk
+        uint32_t t = (uint32_t)(p & 31u);
+        uint32_t take = (uint32_t)(remaining < (uint64_t)(32 - t) ? remaining : (uint64_t)(32 - t));
+        uint32_t mask = low_mask((int)take) << t;
+        uint32_t* chunk = record_words + group * 4;
+        if(comp & 1u) { atomicOr(chunk + 0, mask); }
+        if(comp & 2u) { atomicOr(chunk + 1, mask); }
+        if(comp & 4u) { atomicOr(chunk + 2, mask); }
+        p += take; remaining -= take;
+      }
+    }
+    pos += length;
+  });
+}
+
+// Per-record counts of comps 1..5 (positions beyond `size` hold comp 0 and are never counted).
+__global__ void k0_record_counts(const uint4* __restrict__ records, uint64_t n_records, uint32_t* __restrict__ counts)
+{
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(r >= n_records) { return; }
+  uint32_t local[SIGMA] = { 0, 0, 0, 0, 0, 0 };
+#pragma unroll
+  for(int j = 0; j < 4; j++)
+  {
+    uint4 q = records[4 * r + j];
+#pragma unroll
+    for(uint32_t c = 1; c < SIGMA; c++) { local[c] += __popc(match_mask(q, c)); }
+  }
+#pragma unroll
+  for(uint32_t c = 1; c < SIGMA; c++) { counts[(c - 1) * n_records + r] = local[c]; }
+}
+
+// Packs the five 25-bit superblock-relative counters into the header words and writes the
+// superblock table.
+__global__ void k0_pack_headers(uint32_t* __restrict__ record_words, uint64_t n_records,
+                                const uint64_t* __restrict__ cumulative /* 5 x n_records, exclusive */,
+                                uint64_t* __restrict__ super)
+{
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(r >= n_records) { return; }
+  uint64_t sb = r >> SUPER_RECORD_SHIFT;
+  uint64_t sb_record = sb << SUPER_RECORD_SHIFT;
+  uint64_t rel[SIGMA];
+  uint64_t others = 0;
+#pragma unroll
+  for(uint32_t c = 1; c < SIGMA; c++)
+  {
+    uint64_t base = cumulative[(c - 1) * n_records + sb_record];
+    rel[c] = cumulative[(c - 1) * n_records + r] - base;
+    others += base;
+  }
+  uint64_t lo = rel[1] | (rel[2] << 25) | (rel[3] << 50);
+  uint64_t hi = (rel[3] >> 14) | (rel[4] << 11) | (rel[5] << 36);
+  uint32_t* words = record_words + r * 16;
+  words[3]  = (uint32_t)lo;
+  words[7]  = (uint32_t)(lo >> 32);
+  words[11] = (uint32_t)hi;
+  words[15] = (uint32_t)(hi >> 32);
+  if(r == sb_record)
+  {
+    uint64_t* row = super + sb * SUPER_STRIDE;
+    row[0] = (sb_record << RECORD_SHIFT) - others;
+#pragma unroll
+    for(uint32_t c = 1; c < SIGMA; c++) { row[c] = cumulative[(c - 1) * n_records + sb_record]; }
+    row[6] = 0; row[7] = 0;
+  }
+}
+
+struct CastU64
+{
+  __host__ __device__ __forceinline__ uint64_t operator()(const uint32_t& x) const { return (uint64_t)x; }
+};
+
+int rle_block_starts(const uint8_t* d_rle, uint64_t rle_bytes, uint64_t* d_starts, cudaStream_t stream)
+{
+  uint64_t blocks = div_up(rle_bytes, RLE_BLOCK);
+  BWTM_CUDA(cudaMemsetAsync(d_starts, 0, (blocks + 1) * sizeof(uint64_t), stream));
+  if(blocks == 0) { return BWTM_OK; }
+  k0_block_lengths<<<(unsigned)div_up(blocks, K0_THREADS), K0_THREADS, 0, stream>>>(d_rle, rle_bytes, blocks, d_starts);
+  BWTM_LAUNCH_CHECK();
+  // Exclusive scan over blocks + 1 entries (the last input is 0): d_starts[blocks] = total length.
+  size_t temp_bytes = 0;
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, d_starts, d_starts, blocks + 1, stream));
+  DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(temp.ptr, temp_bytes, d_starts, d_starts, blocks + 1, stream));
+  count_launch(2);
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  return BWTM_OK;
+}
+
+void index_free(bwtm_index* index)
+{
+  if(index == nullptr) { return; }
+  if(index->d_rle != nullptr) { cudaFree(index->d_rle); }
+  if(index->d_records != nullptr) { cudaFree(index->d_records); }
+  if(index->d_super != nullptr) { cudaFree(index->d_super); }
+  delete index;
+}
+
+int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t stream, bwtm_index** out)
+{
+  if(rle_bytes == 0) { set_error("empty BWT"); return BWTM_ERR_ARGUMENT; }
+  uint64_t blocks = div_up(rle_bytes, RLE_BLOCK);
+
+  DeviceBuffer starts; BWTM_TRY(starts.allocate((blocks + 1) * sizeof(uint64_t)));
+  BWTM_TRY(rle_block_starts(d_rle, rle_bytes, starts.as<uint64_t>(), stream));
+  uint64_t size = 0;
+  BWTM_CUDA(cudaMemcpy(&size, starts.as<uint64_t>() + blocks, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if(size == 0) { set_error("BWT decodes to an empty sequence"); return BWTM_ERR_ARGUMENT; }
+
+  uint64_t n_records = (size >> RECORD_SHIFT) + 1;
+  uint64_t n_super = ((n_records - 1) >> SUPER_RECORD_SHIFT) + 1;
+  DeviceBuffer records; BWTM_TRY(records.allocate(n_records * 64));
+  DeviceBuffer super; BWTM_TRY(super.allocate(n_super * SUPER_STRIDE * sizeof(uint64_t)));
+  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, n_records * 64, stream));
+  BWTM_CUDA(cudaMemsetAsync(super.ptr, 0, n_super * SUPER_STRIDE * sizeof(uint64_t), stream));
+
+  k0_fill_planes<<<(unsigned)div_up(blocks, K0_THREADS), K0_THREADS, 0, stream>>>(
+    d_rle, rle_bytes, blocks, starts.as<uint64_t>(), records.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+
+  DeviceBuffer counts; BWTM_TRY(counts.allocate(5 * n_records * sizeof(uint32_t)));
+  DeviceBuffer cumulative; BWTM_TRY(cumulative.allocate(5 * n_records * sizeof(uint64_t)));
+  k0_record_counts<<<(unsigned)div_up(n_records, 256), 256, 0, stream>>>(records.as<uint4>(), n_records, counts.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+
+  size_t temp_bytes = 0;
+  {
+    cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> in(counts.as<uint32_t>(), CastU64());
+    BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, in, cumulative.as<uint64_t>(), n_records, stream));
+  }
+  DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
+  for(int c = 0; c < 5; c++)
+  {
+    cub::TransformInputIterator<uint64_t, CastU64, const uint32_t*> in(counts.as<uint32_t>() + c * n_records, CastU64());
+    BWTM_CUDA(cub::DeviceScan::ExclusiveSum(temp.ptr, temp_bytes, in, cumulative.as<uint64_t>() + c * n_records, n_records, stream));
+    count_launch(2);
+  }
+
+  k0_pack_headers<<<(unsigned)div_up(n_records, 256), 256, 0, stream>>>(
+    records.as<uint32_t>(), n_records, cumulative.as<uint64_t>(), super.as<uint64_t>());
+  BWTM_LAUNCH_CHECK();
+
+  // Totals: exclusive prefix of the last record + its own counts.
+  uint64_t last_cum[5]; uint32_t last_cnt[5];
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  for(int c = 0; c < 5; c++)
+  {
+    BWTM_CUDA(cudaMemcpy(&last_cum[c], cumulative.as<uint64_t>() + c * n_records + (n_records - 1), sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    BWTM_CUDA(cudaMemcpy(&last_cnt[c], counts.as<uint32_t>() + c * n_records + (n_records - 1), sizeof(uint32_t), cudaMemcpyDeviceToHost));
+  }
+
+  bwtm_index* index = new bwtm_index();
+  std::memset(index, 0, sizeof(bwtm_index));
+  BWTM_CUDA(cudaGetDevice(&(index->device)));
+  index->rle_bytes = rle_bytes;
+  index->n_records = n_records; index->n_super = n_super;
+  index->size = size;
+  uint64_t others = 0;
+  for(int c = 1; c < SIGMA; c++) { index->counts[c] = last_cum[c - 1] + last_cnt[c - 1]; others += index->counts[c]; }
+  index->counts[0] = size - others;
+  index->sequences = index->counts[0];
+  index->C[0] = 0;
+  for(int c = 0; c < SIGMA; c++) { index->C[c + 1] = index->C[c] + index->counts[c]; }
+  index->device_bytes = rle_bytes + RLE_PADDING + records.bytes + super.bytes;
+  index->d_rle = d_rle;
+  index->d_records = static_cast<uint4*>(records.detach());
+  index->d_super = static_cast<uint64_t*>(super.detach());
+  *out = index;
+  return BWTM_OK;
+}
+
+//------------------------------------------------------------------------------
+// Query kernels
+
+__global__ void query_rank(DeviceIndex idx, const uint64_t* __restrict__ positions, const uint8_t* __restrict__ comps,
+                           uint64_t n, uint64_t* __restrict__ out)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= n) { return; }
+  out[k] = rank_any(idx, positions[k], comps[k]);
+}
+
+// FMI::LF(i): (C[c] + rank(i, c), c) with c = BWT[i]; (0, 0) for i >= size (bwt.cpp:448-449 returns
+// rank 0 and comp 0, to which LF adds C[0] = 0).
+__global__ void query_lf(DeviceIndex idx, const uint64_t* __restrict__ positions, uint64_t n,
+                         uint64_t* __restrict__ out_positions, uint8_t* __restrict__ out_comps)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= n) { return; }
+  uint64_t i = positions[k];
+  if(i >= idx.size) { out_positions[k] = 0; out_comps[k] = 0; return; }
+  uint32_t comp;
+  uint64_t next = lf_step(idx, i, comp);
+  if(comp == 0) { next = rank_any(idx, i, 0); }
+  out_positions[k] = next; out_comps[k] = (uint8_t)comp;
+}
+
+// K6: FMI::find (fmi.h:195-209), one thread per pattern; writes Range::length of the result.
+__global__ void query_count(DeviceIndex idx, const uint8_t* __restrict__ patterns, const uint64_t* __restrict__ offsets,
+                            uint64_t n, const uint8_t* __restrict__ char2comp, uint64_t* __restrict__ out)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= n) { return; }
+  uint64_t begin = offsets[k], end = offsets[k + 1];
+  if(begin == end) { out[k] = idx.size; return; }   // range (0, size - 1)
+  end--;
+  uint32_t c = patterns[end]; if(char2comp != nullptr) { c = char2comp[c]; }
+  if(c >= SIGMA) { out[k] = 0; return; }
+  uint64_t first = idx.C[c], second = idx.C[c + 1] - 1;
+  while(first + 1 <= second + 1 && end != begin)    // !Range::empty(range), utils.h:80-83
+  {
+    end--;
+    c = patterns[end]; if(char2comp != nullptr) { c = char2comp[c]; }
+    if(c >= SIGMA) { first = 1; second = 0; break; }
+    uint64_t f = idx.C[c] + rank_any(idx, first, c);
+    uint64_t s = idx.C[c] + rank_any(idx, second + 1, c) - 1;
+    first = f; second = s;
+  }
+  out[k] = second + 1 - first;
+}
+
+__global__ void extract_symbols(DeviceIndex idx, uint64_t first, uint64_t count, uint8_t* __restrict__ out)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= count) { return; }
+  uint64_t i = first + k;
+  uint4 q = idx.records[4 * (i >> RECORD_SHIFT) + ((i >> 5) & 3)];
+  uint32_t t = (uint32_t)(i & 31u);
+  out[k] = (uint8_t)(((q.x >> t) & 1u) | (((q.y >> t) & 1u) << 1) | (((q.z >> t) & 1u) << 2));
+}
+
+// Block samples of BWT::build: cumulative counts through RLE block k = rank(start of block k + 1, c).
+__global__ void sample_blocks(DeviceIndex idx, const uint64_t* __restrict__ starts, uint64_t blocks,
+                              uint64_t* __restrict__ block_ends, uint64_t* __restrict__ cumulative)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= blocks) { return; }
+  uint64_t next = starts[k + 1];
+  block_ends[k] = next - 1;
+  for(uint32_t c = 0; c < SIGMA; c++) { cumulative[c * blocks + k] = rank_any(idx, next, c); }
+}
+
+} // namespace bwtm
+
+//------------------------------------------------------------------------------
+// C ABI: library, index, queries
+
+using namespace bwtm;
+
+static int check_device()
+{
+  int count = 0;
+  cudaError_t err = cudaGetDeviceCount(&count);
+  if(err != cudaSuccess || count == 0)
+  {
+    cudaGetLastError();
+    set_error("no CUDA device available (%s); this library has no CPU fallback",
+              err != cudaSuccess ? cudaGetErrorString(err) : "device count is 0");
+    return BWTM_ERR_CUDA;
+  }
+  return BWTM_OK;
+}
+
+extern "C"
+{
+
+const char* bwtm_last_error(void) { return last_error_message.c_str(); }
+const char* bwtm_version(void) { return "bwtm_b200 0.1 (sm_100a)"; }
+
+int bwtm_device_count(int* count)
+{
+  if(count == nullptr) { set_error("count is NULL"); return BWTM_ERR_ARGUMENT; }
+  cudaError_t err = cudaGetDeviceCount(count);
+  if(err != cudaSuccess) { *count = 0; return cuda_failed(err, "cudaGetDeviceCount", __FILE__, __LINE__); }
+  return BWTM_OK;
+}
+
+int bwtm_set_device(int device)
+{
+  BWTM_TRY(check_device());
+  BWTM_CUDA(cudaSetDevice(device));
+  return BWTM_OK;
+}
+
+uint64_t bwtm_kernel_launches(void) { return launch_counter()->load(); }
+
+int bwtm_index_create_device(const void* rle_device, uint64_t rle_bytes, bwtm_index** out)
+{
+  if(rle_device == nullptr || out == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  *out = nullptr;
+  BWTM_TRY(check_device());
+  DeviceBuffer rle; BWTM_TRY(rle.allocate(rle_bytes + RLE_PADDING));
+  BWTM_CUDA(cudaMemcpy(rle.ptr, rle_device, rle_bytes, cudaMemcpyDeviceToDevice));
+  BWTM_CUDA(cudaMemset(rle.as<uint8_t>() + rle_bytes, 0, RLE_PADDING));
+  BWTM_TRY(index_from_device_rle(rle.as<uint8_t>(), rle_bytes, 0, out));
+  rle.detach();
+  return BWTM_OK;
+}
+
+int bwtm_index_create(const uint8_t* rle, uint64_t rle_bytes, const uint64_t* expected_counts, bwtm_index** out)
+{
+  if(rle == nullptr || out == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  *out = nullptr;
+  BWTM_TRY(check_device());
+  DeviceBuffer d_rle; BWTM_TRY(d_rle.allocate(rle_bytes + RLE_PADDING));
+  BWTM_CUDA(cudaMemcpy(d_rle.ptr, rle, rle_bytes, cudaMemcpyHostToDevice));
+  BWTM_CUDA(cudaMemset(d_rle.as<uint8_t>() + rle_bytes, 0, RLE_PADDING));
+  bwtm_index* index = nullptr;
+  BWTM_TRY(index_from_device_rle(d_rle.as<uint8_t>(), rle_bytes, 0, &index));
+  d_rle.detach();
+  if(expected_counts != nullptr)
+  {
+    for(int c = 0; c < SIGMA; c++)
+    {
+      if(expected_counts[c] != index->counts[c])
+      {
+        set_error("count of comp %d is %llu, expected %llu", c,
+                  (unsigned long long)index->counts[c], (unsigned long long)expected_counts[c]);
+        index_free(index);
+        return BWTM_ERR_ARGUMENT;
+      }
+    }
+  }
+  *out = index;
+  return BWTM_OK;
+}
+
+int bwtm_index_destroy(bwtm_index* index)
+{
+  index_free(index);
+  return BWTM_OK;
+}
+
+int bwtm_index_get_info(const bwtm_index* index, bwtm_index_info* info)
+{
+  if(index == nullptr || info == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  info->sequences = index->sequences; info->bases = index->size; info->rle_bytes = index->rle_bytes;
+  for(int c = 0; c < SIGMA; c++) { info->counts[c] = index->counts[c]; }
+  for(int c = 0; c <= SIGMA; c++) { info->C[c] = index->C[c]; }
+  info->device_bytes = index->device_bytes;
+  return BWTM_OK;
+}
+
+int bwtm_index_download(const bwtm_index* index, uint8_t* out_rle, uint64_t capacity, uint64_t* rle_bytes)
+{
+  if(index == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  if(rle_bytes != nullptr) { *rle_bytes = index->rle_bytes; }
+  if(out_rle == nullptr) { return BWTM_OK; }
+  if(capacity < index->rle_bytes) { set_error("output buffer too small"); return BWTM_ERR_CAPACITY; }
+  BWTM_CUDA(cudaMemcpy(out_rle, index->d_rle, index->rle_bytes, cudaMemcpyDeviceToHost));
+  return BWTM_OK;
+}
+
+int bwtm_index_samples(const bwtm_index* index, uint64_t* block_ends, uint64_t* cumulative, uint64_t blocks)
+{
+  if(index == nullptr || block_ends == nullptr || cumulative == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  uint64_t expected = div_up(index->rle_bytes, RLE_BLOCK);
+  if(blocks != expected) { set_error("the index has %llu blocks", (unsigned long long)expected); return BWTM_ERR_ARGUMENT; }
+  DeviceBuffer starts; BWTM_TRY(starts.allocate((blocks + 1) * sizeof(uint64_t)));
+  BWTM_TRY(rle_block_starts(index->d_rle, index->rle_bytes, starts.as<uint64_t>(), 0));
+  DeviceBuffer ends; BWTM_TRY(ends.allocate(blocks * sizeof(uint64_t)));
+  DeviceBuffer cum; BWTM_TRY(cum.allocate(SIGMA * blocks * sizeof(uint64_t)));
+  sample_blocks<<<(unsigned)div_up(blocks, 256), 256>>>(device_view(index), starts.as<uint64_t>(), blocks,
+                                                         ends.as<uint64_t>(), cum.as<uint64_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpy(block_ends, ends.ptr, blocks * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  BWTM_CUDA(cudaMemcpy(cumulative, cum.ptr, SIGMA * blocks * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  return BWTM_OK;
+}
+
+int bwtm_index_extract(const bwtm_index* index, uint64_t first, uint64_t count, uint8_t* out_comps)
+{
+  if(index == nullptr || out_comps == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  if(first > index->size || count > index->size - first) { set_error("range out of bounds"); return BWTM_ERR_ARGUMENT; }
+  if(count == 0) { return BWTM_OK; }
+  DeviceBuffer out; BWTM_TRY(out.allocate(count));
+  extract_symbols<<<(unsigned)div_up(count, 256), 256>>>(device_view(index), first, count, out.as<uint8_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpy(out_comps, out.ptr, count, cudaMemcpyDeviceToHost));
+  return BWTM_OK;
+}
+
+int bwtm_index_hash(const bwtm_index* index, uint64_t* hash)
+{
+  if(index == nullptr || hash == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  // FNV-1a is inherently sequential; the symbols are extracted on the device and folded on the host.
+  const uint64_t CHUNK = 64ull << 20;
+  std::vector<uint8_t> buffer(index->size < CHUNK ? index->size : CHUNK);
+  uint64_t h = 0xcbf29ce484222325ULL;
+  for(uint64_t first = 0; first < index->size; first += CHUNK)
+  {
+    uint64_t count = (index->size - first < CHUNK ? index->size - first : CHUNK);
+    BWTM_TRY(bwtm_index_extract(index, first, count, buffer.data()));
+    for(uint64_t i = 0; i < count; i++) { h = (h ^ buffer[i]) * 0x100000001b3ULL; }
+  }
+  *hash = h;
+  return BWTM_OK;
+}
+
+int bwtm_rank(const bwtm_index* index, const uint64_t* positions, const uint8_t* comps, uint64_t n, uint64_t* out_ranks)
+{
+  if(index == nullptr || positions == nullptr || comps == nullptr || out_ranks == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  if(n == 0) { return BWTM_OK; }
+  DeviceBuffer pos, cmp, res;
+  BWTM_TRY(pos.allocate(n * 8)); BWTM_TRY(cmp.allocate(n)); BWTM_TRY(res.allocate(n * 8));
+  BWTM_CUDA(cudaMemcpy(pos.ptr, positions, n * 8, cudaMemcpyHostToDevice));
+  BWTM_CUDA(cudaMemcpy(cmp.ptr, comps, n, cudaMemcpyHostToDevice));
+  query_rank<<<(unsigned)div_up(n, 256), 256>>>(device_view(index), pos.as<uint64_t>(), cmp.as<uint8_t>(), n, res.as<uint64_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpy(out_ranks, res.ptr, n * 8, cudaMemcpyDeviceToHost));
+  return BWTM_OK;
+}
+
+int bwtm_lf(const bwtm_index* index, const uint64_t* positions, uint64_t n, uint64_t* out_positions, uint8_t* out_comps)
+{
+  if(index == nullptr || positions == nullptr || out_positions == nullptr || out_comps == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  if(n == 0) { return BWTM_OK; }
+  DeviceBuffer pos, res, cmp;
+  BWTM_TRY(pos.allocate(n * 8)); BWTM_TRY(res.allocate(n * 8)); BWTM_TRY(cmp.allocate(n));
+  BWTM_CUDA(cudaMemcpy(pos.ptr, positions, n * 8, cudaMemcpyHostToDevice));
+  query_lf<<<(unsigned)div_up(n, 256), 256>>>(device_view(index), pos.as<uint64_t>(), n, res.as<uint64_t>(), cmp.as<uint8_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpy(out_positions, res.ptr, n * 8, cudaMemcpyDeviceToHost));
+  BWTM_CUDA(cudaMemcpy(out_comps, cmp.ptr, n, cudaMemcpyDeviceToHost));
+  return BWTM_OK;
+}
+
+int bwtm_count(const bwtm_index* index, const uint8_t* patterns, const uint64_t* offsets, uint64_t n,
+               const uint8_t* char2comp, uint64_t* out_counts)
+{
+  if(index == nullptr || offsets == nullptr || out_counts == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  if(n == 0) { return BWTM_OK; }
+  uint64_t total = offsets[n];
+  if(total > 0 && patterns == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  DeviceBuffer pat, off, map, res;
+  BWTM_TRY(pat.allocate(total)); BWTM_TRY(off.allocate((n + 1) * 8)); BWTM_TRY(res.allocate(n * 8));
+  if(total > 0) { BWTM_CUDA(cudaMemcpy(pat.ptr, patterns, total, cudaMemcpyHostToDevice)); }
+  BWTM_CUDA(cudaMemcpy(off.ptr, offsets, (n + 1) * 8, cudaMemcpyHostToDevice));
+  if(char2comp != nullptr)
+  {
+    BWTM_TRY(map.allocate(256));
+    BWTM_CUDA(cudaMemcpy(map.ptr, char2comp, 256, cudaMemcpyHostToDevice));
+  }
+  query_count<<<(unsigned)div_up(n, 128), 128>>>(device_view(index), pat.as<uint8_t>(), off.as<uint64_t>(), n,
+                                                  char2comp != nullptr ? map.as<uint8_t>() : nullptr, res.as<uint64_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpy(out_counts, res.ptr, n * 8, cudaMemcpyDeviceToHost));
+  return BWTM_OK;
+}
+
+} // extern "C"

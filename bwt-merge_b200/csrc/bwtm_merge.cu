@@ -1,0 +1,707 @@
+// K4 interleave, K3 run detection, K5 byte-exact encoder, and the merge entry point.
+//
+// Replaces mergeBWT (bwt.cpp:215-282) and its RunBuffer + Run::write output path:
+//   * the merged sequence M has B[j] at position j + RA[j] and A[i] at position i + #{j : RA[j] <= i}
+//     ("before B[j] come RA[j] symbols of A", bwt.cpp:234-261), RA being the sorted rank array;
+//   * M is cut into tiles of TILE positions; a merge-path search on the diagonal gives every tile
+//     its first A and B index, a shared-memory bitmap marks which positions of the tile come from B,
+//     and every thread fetches 16 consecutive symbols from the position-addressed records;
+//   * maximal runs of M (what the reference's RunBuffer produces, utils.h:121-142) are found with a
+//     device run-length encode;
+//   * Run::write (support.h:256-282) is sequential through the output offset modulo 64 only for
+//     runs of length >= 42: runs shorter than that always take one byte.  The long runs are
+//     compacted, the writer is evaluated for all 64 entry offsets per tile of long runs (a 64-state
+//     transducer), the tile maps are composed by a scan, and every run is then written at its
+//     exact byte offset.
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+
+#include <cub/cub.cuh>
+
+#include "bwtm_merge.cuh"
+
+namespace bwtm
+{
+
+constexpr int TILE        = 4096;
+constexpr int IL_THREADS  = 256;
+constexpr int PER_THREAD  = TILE / IL_THREADS;   // 16
+constexpr int LONG_TILE   = 1024;                // long runs per transducer tile
+
+//------------------------------------------------------------------------------
+// K4
+
+template<class KeyT>
+__global__ void k4_partition(const KeyT* __restrict__ keys, uint64_t key_base, uint64_t key_count,
+                             uint64_t begin, uint64_t end, uint64_t tiles, uint64_t* __restrict__ tile_j)
+{
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(t > tiles) { return; }
+  uint64_t d = begin + t * TILE;
+  if(d > end) { d = end; }
+  // Number of B symbols placed before merged position d: j + RA[j] is strictly increasing in j.
+  uint64_t lo = 0, hi = key_count;
+  while(lo < hi)
+  {
+    uint64_t mid = lo + (hi - lo) / 2;
+    if(key_base + mid + (uint64_t)keys[mid] < d) { lo = mid + 1; } else { hi = mid; }
+  }
+  tile_j[t] = key_base + lo;
+}
+
+__device__ __forceinline__ uint32_t fetch_symbol(const DeviceIndex& idx, uint64_t pos, uint64_t& cached_group, uint4& cached)
+{
+  uint64_t group = pos >> 5;
+  if(group != cached_group) { cached = __ldg(idx.records + group); cached_group = group; }
+  uint32_t t = (uint32_t)(pos & 31u);
+  return ((cached.x >> t) & 1u) | (((cached.y >> t) & 1u) << 1) | (((cached.z >> t) & 1u) << 2);
+}
+
+template<class KeyT>
+__global__ void __launch_bounds__(IL_THREADS)
+k4_interleave(DeviceIndex a, DeviceIndex b, const KeyT* __restrict__ keys, uint64_t key_base,
+              const uint64_t* __restrict__ tile_j, uint64_t begin, uint64_t end, uint8_t* __restrict__ merged)
+{
+  __shared__ uint32_t bitmap[TILE / 32];
+  __shared__ uint32_t prefix[TILE / 32];
+
+  const int tid = threadIdx.x;
+  uint64_t d0 = begin + (uint64_t)blockIdx.x * TILE;
+  uint64_t d1 = (d0 + TILE < end ? d0 + TILE : end);
+  uint64_t j0 = tile_j[blockIdx.x], j1 = tile_j[blockIdx.x + 1];
+  uint64_t i0 = d0 - j0;
+
+  if(tid < TILE / 32) { bitmap[tid] = 0; }
+  __syncthreads();
+  for(uint64_t k = tid; k < j1 - j0; k += IL_THREADS)
+  {
+    uint64_t j = j0 + k;
+    uint32_t q = (uint32_t)(j + (uint64_t)keys[j - key_base] - d0);
+    atomicOr(&bitmap[q >> 5], 1u << (q & 31u));
+  }
+  __syncthreads();
+  if(tid < 32)
+  {
+    uint32_t local[4], sum = 0;
+#pragma unroll
+    for(int w = 0; w < 4; w++) { local[w] = sum; sum += __popc(bitmap[tid * 4 + w]); }
+    uint32_t inclusive = sum;
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+      uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+      if(tid >= offset) { inclusive += v; }
+    }
+    uint32_t exclusive = inclusive - sum;
+#pragma unroll
+    for(int w = 0; w < 4; w++) { prefix[tid * 4 + w] = exclusive + local[w]; }
+  }
+  __syncthreads();
+
+  uint32_t p0 = tid * PER_THREAD;
+  uint32_t word = p0 >> 5, shift = p0 & 31u;
+  uint32_t bits = bitmap[word];
+  uint32_t before = prefix[word] + __popc(bits & low_mask((int)shift));
+  uint32_t flags = (bits >> shift) & 0xFFFFu;
+  uint64_t jb = j0 + before, ia = i0 + p0 - before;
+  int valid = 0;
+  if(d0 + p0 < d1) { uint64_t left = d1 - d0 - p0; valid = (left < (uint64_t)PER_THREAD ? (int)left : PER_THREAD); }
+
+  uint32_t w[4] = { 0, 0, 0, 0 };
+  uint64_t group_a = ~0ull, group_b = ~0ull;
+  uint4 chunk_a = make_uint4(0, 0, 0, 0), chunk_b = make_uint4(0, 0, 0, 0);
+#pragma unroll
+  for(int s = 0; s < PER_THREAD; s++)
+  {
+    if(s < valid)
+    {
+      uint32_t sym;
+      if((flags >> s) & 1u) { sym = fetch_symbol(b, jb, group_b, chunk_b); jb++; }
+      else                  { sym = fetch_symbol(a, ia, group_a, chunk_a); ia++; }
+      w[s >> 2] |= sym << (8 * (s & 3));
+    }
+  }
+  *reinterpret_cast<uint4*>(merged + (d0 - begin) + p0) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+//------------------------------------------------------------------------------
+// K5: Run::write (support.h:256-282)
+
+__device__ __forceinline__ uint32_t bytecode_length(uint64_t v)   // bytes ByteCode::write emits (support.h:203-212)
+{
+  uint32_t n = 1;
+  while(v > 0x7Fu) { v >>= 7; n++; }
+  return n;
+}
+
+// Bytes emitted for a run of length >= MAX_RUN that starts at output offset `state` (mod 64).
+__device__ __forceinline__ uint32_t long_run_bytes(uint64_t length, uint32_t state)
+{
+  uint32_t bytes = 0;
+  while(length > 0)
+  {
+    if(length < (uint64_t)MAX_RUN) { bytes++; break; }
+    uint32_t remaining = RLE_BLOCK - state;
+    uint32_t basic = (remaining > 1 ? MAX_RUN : MAX_RUN - 1);
+    length -= basic; bytes++; state = (state + 1) & 63u; remaining--;
+    if(remaining > 0)
+    {
+      uint64_t extension = length;
+      uint32_t nb = bytecode_length(extension);
+      if(nb > remaining) { extension = (1ull << (7 * remaining)) - 1; nb = remaining; }  // bit_length(length) > 7 * remaining
+      length -= extension; bytes += nb; state = (state + nb) & 63u;
+    }
+  }
+  return bytes;
+}
+
+// Writes the run at absolute output offset `offset`; returns the bytes written.
+__device__ __forceinline__ uint32_t write_run(uint8_t* __restrict__ out, uint64_t offset, uint32_t comp, uint64_t length)
+{
+  uint64_t pos = offset;
+  while(length > 0)
+  {
+    if(length < (uint64_t)MAX_RUN) { out[pos++] = (uint8_t)(comp + SIGMA * (length - 1)); break; }
+    uint32_t remaining = RLE_BLOCK - (uint32_t)(pos & 63u);
+    uint32_t basic = (remaining > 1 ? MAX_RUN : MAX_RUN - 1);
+    out[pos++] = (uint8_t)(comp + SIGMA * (basic - 1)); length -= basic; remaining--;
+    if(remaining > 0)
+    {
+      uint64_t extension = length;
+      if(bytecode_length(extension) > remaining) { extension = (1ull << (7 * remaining)) - 1; }
+      length -= extension;
+      while(extension > 0x7Fu) { out[pos++] = (uint8_t)((extension & 0x7Fu) | 0x80u); extension >>= 7; }
+      out[pos++] = (uint8_t)extension;
+    }
+  }
+  return (uint32_t)(pos - offset);
+}
+
+// Sequential glue between slabs: the RunBuffer state (pending maximal run) and Run::write for it.
+__global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ len,
+                         uint64_t m, uint8_t* __restrict__ out, int finish)
+{
+  if(blockIdx.x != 0 || threadIdx.x != 0) { return; }
+  ctl->start = 0; ctl->count = 0; ctl->n_short = 0; ctl->n_long = 0; ctl->long_bytes = 0;
+  if(finish)
+  {
+    if(ctl->carry_len > 0)
+    {
+      ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
+      ctl->runs_total++; ctl->carry_len = 0;
+    }
+    ctl->slab_base = ctl->out_size;
+    return;
+  }
+  bool merged = (ctl->carry_len > 0 && sym[0] == ctl->carry_sym);
+  if(merged && m == 1) { ctl->carry_len += len[0]; ctl->start = 1; ctl->slab_base = ctl->out_size; return; }
+  if(merged)
+  {
+    ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len + len[0]);
+    ctl->runs_total++; ctl->start = 1;
+  }
+  else if(ctl->carry_len > 0)
+  {
+    ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
+    ctl->runs_total++;
+  }
+  ctl->carry_sym = sym[m - 1]; ctl->carry_len = len[m - 1];
+  ctl->count = (m - 1) - ctl->start;
+  ctl->slab_base = ctl->out_size;
+}
+
+struct RunClass   // 1 in the low word for a short run, 1 in the high word for a long run
+{
+  __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t& length) const
+  {
+    return (length < (uint32_t)MAX_RUN ? 1ull : (1ull << 32));
+  }
+};
+
+__global__ void enc_collect_long(EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+                                 uint64_t count, uint32_t* __restrict__ long_list)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= count) { return; }
+  uint32_t length = len[k];
+  unsigned long long s = scan[k];
+  bool is_long = (length >= (uint32_t)MAX_RUN);
+  if(is_long) { long_list[s >> 32] = (uint32_t)k; }
+  if(k == count - 1)
+  {
+    ctl->n_short = (s & 0xFFFFFFFFull) + (is_long ? 0 : 1);
+    ctl->n_long = (s >> 32) + (is_long ? 1 : 0);
+  }
+}
+
+// Transducer tile maps: bytes produced by the tile's long runs for each of the 64 residues of
+// "bytes produced by earlier long runs".
+__global__ void __launch_bounds__(64)
+enc_tile_maps(const EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+              const uint32_t* __restrict__ long_list, uint64_t n_long, uint32_t* __restrict__ tile_bytes)
+{
+  uint32_t base_state = (uint32_t)(ctl->slab_base & 63u);
+  uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
+  uint64_t last = (first + LONG_TILE < n_long ? first + LONG_TILE : n_long);
+  uint32_t p = threadIdx.x;
+  for(uint64_t k = first; k < last; k++)
+  {
+    uint32_t idx = long_list[k];
+    uint32_t state = (base_state + (uint32_t)scan[idx] + p) & 63u;
+    p += long_run_bytes(len[idx], state);
+  }
+  tile_bytes[(uint64_t)blockIdx.x * 64 + threadIdx.x] = p - threadIdx.x;
+}
+
+__global__ void enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint64_t tiles,
+                              unsigned long long* __restrict__ tile_entry)
+{
+  if(blockIdx.x != 0 || threadIdx.x != 0) { return; }
+  unsigned long long p = 0;
+  for(uint64_t t = 0; t < tiles; t++)
+  {
+    tile_entry[t] = p;
+    p += tile_bytes[t * 64 + (p & 63u)];
+  }
+  ctl->long_bytes = p;
+  ctl->out_size = ctl->slab_base + ctl->n_short + p;
+  ctl->runs_total += ctl->count;
+}
+
+__global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+                                 const uint32_t* __restrict__ long_list, uint64_t n_long, uint64_t tiles,
+                                 const unsigned long long* __restrict__ tile_entry, uint32_t* __restrict__ long_offset)
+{
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= tiles) { return; }
+  uint32_t base_state = (uint32_t)(ctl->slab_base & 63u);
+  uint64_t first = t * LONG_TILE;
+  uint64_t last = (first + LONG_TILE < n_long ? first + LONG_TILE : n_long);
+  unsigned long long p = tile_entry[t];
+  for(uint64_t k = first; k < last; k++)
+  {
+    uint32_t idx = long_list[k];
+    long_offset[k] = (uint32_t)p;
+    uint32_t state = (base_state + (uint32_t)scan[idx] + (uint32_t)p) & 63u;
+    p += long_run_bytes(len[idx], state);
+  }
+}
+
+__global__ void enc_write(const EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ len,
+                          const unsigned long long* __restrict__ scan, const uint32_t* __restrict__ long_offset,
+                          uint64_t count, uint8_t* __restrict__ out)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= count) { return; }
+  unsigned long long s = scan[k];
+  uint64_t longs_before = s >> 32;
+  uint64_t bytes_before = (s & 0xFFFFFFFFull) + (longs_before < ctl->n_long ? (uint64_t)long_offset[longs_before] : ctl->long_bytes);
+  uint64_t offset = ctl->slab_base + bytes_before;
+  uint32_t length = len[k], comp = sym[k];
+  if(length < (uint32_t)MAX_RUN) { out[offset] = (uint8_t)(comp + SIGMA * (length - 1)); }
+  else { write_run(out, offset, comp, length); }
+}
+
+//------------------------------------------------------------------------------
+// Host orchestration
+
+int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cudaStream_t stream)
+{
+  if(needed <= out->capacity) { return BWTM_OK; }
+  uint64_t capacity = std::max(needed + (needed >> 2), (uint64_t)(1 << 20));
+  DeviceBuffer bigger; BWTM_TRY(bigger.allocate(capacity));
+  if(out->ptr != nullptr && valid_bytes > 0)
+  {
+    BWTM_CUDA(cudaMemcpyAsync(bigger.ptr, out->ptr, valid_bytes, cudaMemcpyDeviceToDevice, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+  }
+  if(out->ptr != nullptr) { cudaFree(out->ptr); }
+  out->ptr = static_cast<uint8_t*>(bigger.detach());
+  out->capacity = capacity;
+  return BWTM_OK;
+}
+
+struct EventTimer
+{
+  cudaEvent_t begin, end;
+  cudaStream_t stream;
+  bool ok;
+  explicit EventTimer(cudaStream_t s) : stream(s)
+  {
+    ok = (cudaEventCreate(&begin) == cudaSuccess && cudaEventCreate(&end) == cudaSuccess);
+  }
+  ~EventTimer() { if(ok) { cudaEventDestroy(begin); cudaEventDestroy(end); } }
+  void start() { if(ok) { cudaEventRecord(begin, stream); } }
+  float stop()
+  {
+    if(!ok) { return 0.0f; }
+    cudaEventRecord(end, stream); cudaEventSynchronize(end);
+    float ms = 0.0f; cudaEventElapsedTime(&ms, begin, end); return ms;
+  }
+};
+
+int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
+{
+  max_symbols = max_symbols_;
+  uint64_t max_long = max_symbols / MAX_RUN + 1;
+  uint64_t max_long_tiles = div_up(max_long, LONG_TILE);
+  BWTM_TRY(run_sym.allocate(max_symbols));
+  BWTM_TRY(run_len.allocate(max_symbols * sizeof(uint32_t)));
+  BWTM_TRY(num_runs.allocate(sizeof(uint64_t)));
+  BWTM_TRY(scan.allocate(max_symbols * sizeof(unsigned long long)));
+  BWTM_TRY(long_list.allocate(max_long * sizeof(uint32_t)));
+  BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
+  BWTM_TRY(tile_bytes.allocate(max_long_tiles * 64 * sizeof(uint32_t)));
+  BWTM_TRY(tile_entry.allocate(max_long_tiles * sizeof(unsigned long long)));
+
+  size_t rle_temp = 0, scan_temp = 0;
+  BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_temp, (const uint8_t*)nullptr, run_sym.as<uint8_t>(),
+                                                run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)max_symbols, stream));
+  {
+    cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes(run_len.as<uint32_t>(), RunClass());
+    BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, classes, scan.as<unsigned long long>(), (int64_t)max_symbols, stream));
+  }
+  BWTM_TRY(cub_temp.allocate(std::max(rle_temp, scan_temp)));
+  return BWTM_OK;
+}
+
+// K3 + K5 for `symbols` consecutive symbols of the sequence being written.
+int SlabEncoder::encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+{
+  if(symbols == 0) { return BWTM_OK; }
+  if(symbols > max_symbols) { set_error("slab of %llu symbols exceeds the encoder capacity", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
+  size_t temp_bytes = cub_temp.bytes;
+  EncodeControl ctl;
+
+  // K3: maximal runs of the slab
+  BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, sizeof(uint64_t), stream));
+  BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(cub_temp.ptr, temp_bytes, d_symbols, run_sym.as<uint8_t>(),
+                                                run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)symbols, stream));
+  count_launch(3);
+  uint64_t m = 0;
+  BWTM_CUDA(cudaMemcpyAsync(&m, num_runs.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  if(m == 0) { set_error("run-length encode produced no runs for %llu symbols", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
+
+  // K5
+  BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.out_size, stream));
+  enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_len.as<uint32_t>(), m, out->ptr, 0);
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  if(ctl.count == 0) { return BWTM_OK; }
+
+  uint64_t count = ctl.count;
+  const uint8_t* sym = run_sym.as<uint8_t>() + ctl.start;
+  const uint32_t* len = run_len.as<uint32_t>() + ctl.start;
+  cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes(len, RunClass());
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, classes, scan.as<unsigned long long>(), (int64_t)count, stream));
+  count_launch(2);
+  enc_collect_long<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), count, long_list.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  uint64_t n_long = ctl.n_long;
+  uint64_t long_tiles = div_up(n_long, LONG_TILE);
+  if(long_tiles > 0)
+  {
+    enc_tile_maps<<<(unsigned)long_tiles, 64, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), n_long, tile_bytes.as<uint32_t>());
+    BWTM_LAUNCH_CHECK();
+  }
+  enc_tile_scan<<<1, 1, 0, stream>>>(d_control, tile_bytes.as<uint32_t>(), long_tiles, tile_entry.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  if(long_tiles > 0)
+  {
+    enc_long_offsets<<<(unsigned)div_up(long_tiles, 128), 128, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(),
+                                                                           n_long, long_tiles, tile_entry.as<unsigned long long>(), long_offset.as<uint32_t>());
+    BWTM_LAUNCH_CHECK();
+  }
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.slab_base, stream));
+  enc_write<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(d_control, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), count, out->ptr);
+  BWTM_LAUNCH_CHECK();
+  return BWTM_OK;
+}
+
+// Flushes the pending run (bwt.cpp:279-281).
+int SlabEncoder::finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+{
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.out_size, stream));
+  enc_head<<<1, 1, 0, stream>>>(d_control, nullptr, nullptr, 0, out->ptr, 1);
+  BWTM_LAUNCH_CHECK();
+  return BWTM_OK;
+}
+
+uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total)
+{
+  if(slab_symbols == 0) { slab_symbols = 1ull << 30; }
+  slab_symbols = std::min(slab_symbols, (uint64_t)1 << 30);
+  slab_symbols = div_up(slab_symbols, TILE) * TILE;
+  return std::min(slab_symbols, div_up(std::max(total, (uint64_t)1), TILE) * TILE);
+}
+
+template<class KeyT>
+int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
+                     uint64_t begin, uint64_t end, uint64_t slab_symbols,
+                     OutputBuffer* out, EncodeControl* d_control, bool finish,
+                     float* interleave_ms, float* encode_ms, cudaStream_t stream)
+{
+  slab_symbols = clamp_slab(slab_symbols, end - begin);
+  uint64_t max_tiles = slab_symbols / TILE;
+  DeviceBuffer merged, tile_j;
+  BWTM_TRY(merged.allocate(slab_symbols));
+  BWTM_TRY(tile_j.allocate((max_tiles + 1) * sizeof(uint64_t)));
+  SlabEncoder encoder;
+  BWTM_TRY(encoder.init(slab_symbols, stream));
+
+  DeviceIndex va = device_view(a), vb = device_view(b);
+  EventTimer timer(stream);
+
+  for(uint64_t p0 = begin; p0 < end; p0 += slab_symbols)
+  {
+    uint64_t p1 = std::min(p0 + slab_symbols, end);
+    uint64_t symbols = p1 - p0;
+    uint64_t tiles = div_up(symbols, TILE);
+
+    timer.start();
+    k4_partition<KeyT><<<(unsigned)div_up(tiles + 1, 256), 256, 0, stream>>>(d_keys, key_base, key_count, p0, p1, tiles, tile_j.as<uint64_t>());
+    BWTM_LAUNCH_CHECK();
+    k4_interleave<KeyT><<<(unsigned)tiles, IL_THREADS, 0, stream>>>(va, vb, d_keys, key_base, tile_j.as<uint64_t>(), p0, p1, merged.as<uint8_t>());
+    BWTM_LAUNCH_CHECK();
+    *interleave_ms += timer.stop();
+
+    timer.start();
+    BWTM_TRY(encoder.encode(merged.as<uint8_t>(), symbols, out, d_control, stream));
+    *encode_ms += timer.stop();
+  }
+
+  if(finish)
+  {
+    timer.start();
+    BWTM_TRY(encoder.finish(out, d_control, stream));
+    *encode_ms += timer.stop();
+  }
+  return BWTM_OK;
+}
+
+template int interleave_range<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
+                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t);
+template int interleave_range<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
+                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t);
+
+//------------------------------------------------------------------------------
+
+static int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } return (n == 0 ? 1 : n); }
+
+template<class KeyT>
+__global__ void count_distinct(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ result)
+{
+  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool boundary = (k < n) && (k == 0 || keys[k] != keys[k - 1]);
+  unsigned mask = __ballot_sync(0xFFFFFFFFu, boundary);
+  if((threadIdx.x & 31) == 0 && mask != 0) { atomicAdd(result, (unsigned long long)__popc(mask)); }
+}
+
+// Wraps freshly encoded RLE bytes into an index (K0 unless skipped). `counts` (6 values) are the
+// expected per-comp counts, or NULL.
+static int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
+                        cudaStream_t stream, bwtm_index** result)
+{
+  DeviceBuffer exact; BWTM_TRY(exact.allocate(rle_bytes + RLE_PADDING));
+  BWTM_CUDA(cudaMemcpyAsync(exact.ptr, out->ptr, rle_bytes, cudaMemcpyDeviceToDevice, stream));
+  BWTM_CUDA(cudaMemsetAsync(exact.as<uint8_t>() + rle_bytes, 0, RLE_PADDING, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  cudaFree(out->ptr); out->ptr = nullptr; out->capacity = 0;
+
+  if(!skip_index)
+  {
+    BWTM_TRY(index_from_device_rle(exact.as<uint8_t>(), rle_bytes, stream, result));
+    exact.detach();
+    bwtm_index* m = *result;
+    for(int c = 0; counts != nullptr && c < SIGMA; c++)
+    {
+      if(m->counts[c] != counts[c])
+      {
+        set_error("encoded count of comp %d is %llu, expected %llu", c, (unsigned long long)m->counts[c],
+                  (unsigned long long)counts[c]);
+        index_free(m); *result = nullptr;
+        return BWTM_ERR_INTERNAL;
+      }
+    }
+    return BWTM_OK;
+  }
+
+  bwtm_index* m = new bwtm_index();
+  std::memset(m, 0, sizeof(bwtm_index));
+  cudaGetDevice(&(m->device));
+  m->d_rle = static_cast<uint8_t*>(exact.detach()); m->rle_bytes = rle_bytes;
+  m->sequences = sequences;                                                   // bwt.cpp:305-306
+  for(int c = 0; c < SIGMA; c++) { m->counts[c] = counts[c]; m->size += counts[c]; }
+  m->C[0] = 0;
+  for(int c = 0; c < SIGMA; c++) { m->C[c + 1] = m->C[c] + m->counts[c]; }  // fmi.cpp:367-368
+  m->device_bytes = rle_bytes + RLE_PADDING;
+  *result = m;
+  return BWTM_OK;
+}
+
+int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out)
+{
+  if(n == 0) { set_error("empty sequence"); return BWTM_ERR_ARGUMENT; }
+  uint64_t slab = clamp_slab(slab_symbols, n);
+  SlabEncoder encoder; BWTM_TRY(encoder.init(slab, stream));
+  DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
+  BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
+  OutputBuffer buffer = { nullptr, 0 };
+  int rc = ensure_capacity(&buffer, n / 4 + (1 << 20), 0, stream);
+  for(uint64_t p0 = 0; rc == BWTM_OK && p0 < n; p0 += slab)
+  {
+    rc = encoder.encode(d_symbols + p0, std::min(slab, n - p0), &buffer, control.as<EncodeControl>(), stream);
+  }
+  if(rc == BWTM_OK) { rc = encoder.finish(&buffer, control.as<EncodeControl>(), stream); }
+  EncodeControl ctl;
+  if(rc == BWTM_OK && cudaMemcpy(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost) != cudaSuccess)
+  {
+    set_error("cannot read the encoder state"); rc = BWTM_ERR_CUDA;
+  }
+  if(rc == BWTM_OK) { rc = finish_index(&buffer, ctl.out_size, nullptr, 0, false, stream, out); }
+  if(buffer.ptr != nullptr) { cudaFree(buffer.ptr); }
+  return rc;
+}
+
+template<class KeyT>
+static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+                      bwtm_index** result, bwtm_timings* timings)
+{
+  cudaStream_t stream = 0;
+  uint64_t n_b = b->size;
+  DeviceBuffer keys, alt;
+  BWTM_TRY(keys.allocate(n_b * sizeof(KeyT)));
+  BWTM_TRY(alt.allocate(n_b * sizeof(KeyT)));
+
+  EventTimer timer(stream);
+  timer.start();
+  uint64_t emitted = 0;
+  BWTM_TRY(walk_sequences<KeyT>(a, b, 0, b->sequences - 1, keys.as<KeyT>(), n_b, &emitted, stream));
+  timings->search_seconds = timer.stop() * 1e-3;
+  timings->walk_kernel_launches = 1;
+  if(emitted != n_b)
+  {
+    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
+              (unsigned long long)emitted, (unsigned long long)n_b);
+    return BWTM_ERR_INTERNAL;
+  }
+  timings->ra_values = emitted;
+
+  timer.start();
+  KeyT* sorted = nullptr;
+  BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream));
+  timings->sort_seconds = timer.stop() * 1e-3;
+  if(sorted == keys.as<KeyT>()) { alt.release(); } else { keys.release(); }
+
+  {
+    DeviceBuffer distinct; BWTM_TRY(distinct.allocate(sizeof(unsigned long long)));
+    BWTM_CUDA(cudaMemsetAsync(distinct.ptr, 0, sizeof(unsigned long long), stream));
+    count_distinct<KeyT><<<(unsigned)div_up(n_b, 256), 256, 0, stream>>>(sorted, n_b, distinct.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+    unsigned long long runs = 0;
+    BWTM_CUDA(cudaMemcpyAsync(&runs, distinct.ptr, sizeof(runs), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    timings->ra_runs = runs;
+  }
+
+  DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
+  BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
+  OutputBuffer out = { nullptr, 0 };
+  int rc = ensure_capacity(&out, a->rle_bytes + b->rle_bytes + ((a->rle_bytes + b->rle_bytes) >> 2) + (1 << 20), 0, stream);
+  float interleave_ms = 0.0f, encode_ms = 0.0f;
+  if(rc == BWTM_OK)
+  {
+    rc = interleave_range<KeyT>(a, b, sorted, 0, n_b, 0, a->size + b->size, options->slab_symbols,
+                                &out, control.as<EncodeControl>(), true, &interleave_ms, &encode_ms, stream);
+  }
+  if(rc != BWTM_OK) { if(out.ptr != nullptr) { cudaFree(out.ptr); } return rc; }
+  timings->interleave_seconds = interleave_ms * 1e-3;
+  timings->encode_seconds = encode_ms * 1e-3;
+  keys.release(); alt.release();
+
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpy(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost));
+  timings->merged_runs = ctl.runs_total;
+  timings->merged_bytes = ctl.out_size;
+
+  timer.start();
+  uint64_t counts[SIGMA];
+  for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
+  rc = finish_index(&out, ctl.out_size, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
+  if(out.ptr != nullptr) { cudaFree(out.ptr); }
+  timings->index_seconds = timer.stop() * 1e-3;
+  return rc;
+}
+
+int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+                bwtm_index** result, bwtm_timings* timings)
+{
+  if(a->size < 0xFFFFFFFFull) { return merge_impl<uint32_t>(a, b, options, result, timings); }
+  return merge_impl<uint64_t>(a, b, options, result, timings);
+}
+
+} // namespace bwtm
+
+//------------------------------------------------------------------------------
+// C ABI
+
+using namespace bwtm;
+
+extern "C"
+{
+
+int bwtm_merge(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options, bwtm_index** out, bwtm_timings* timings)
+{
+  bwtm_merge_options defaults; std::memset(&defaults, 0, sizeof(defaults));
+  if(options == nullptr) { options = &defaults; }
+  bwtm_timings local; std::memset(&local, 0, sizeof(local));
+  bool keep = (options->keep_inputs != 0);
+
+  int rc = BWTM_OK;
+  if(a == nullptr || b == nullptr || out == nullptr) { set_error("null argument"); rc = BWTM_ERR_ARGUMENT; }
+  else if(a->d_records == nullptr || b->d_records == nullptr) { set_error("an input has no rank structure (it was built with skip_index)"); rc = BWTM_ERR_ARGUMENT; }
+  else if(b->sequences == 0) { set_error("the inserted BWT has no sequences"); rc = BWTM_ERR_ARGUMENT; }
+  if(rc == BWTM_OK)
+  {
+    *out = nullptr;
+    uint64_t launches_before = bwtm_kernel_launches();
+    auto start = std::chrono::steady_clock::now();
+    rc = merge_local(a, b, options, out, &local);
+    cudaDeviceSynchronize();
+    local.total_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    local.kernel_launches = bwtm_kernel_launches() - launches_before;
+  }
+  if(!keep) { index_free(a); index_free(b); }
+  if(timings != nullptr) { *timings = local; }
+  return rc;
+}
+
+int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                    uint64_t* out_sorted, uint64_t capacity, uint64_t* n_values)
+{
+  if(a == nullptr || b == nullptr || out_sorted == nullptr || n_values == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  if(seq_first > seq_last || seq_last >= b->sequences) { set_error("invalid sequence range"); return BWTM_ERR_ARGUMENT; }
+  DeviceBuffer keys, alt;
+  BWTM_TRY(keys.allocate(capacity * sizeof(uint64_t)));
+  BWTM_TRY(alt.allocate(capacity * sizeof(uint64_t)));
+  uint64_t emitted = 0;
+  BWTM_TRY(walk_sequences<uint64_t>(a, b, seq_first, seq_last, keys.as<uint64_t>(), capacity, &emitted, 0));
+  uint64_t* sorted = nullptr;
+  BWTM_TRY(sort_keys<uint64_t>(keys.as<uint64_t>(), alt.as<uint64_t>(), emitted, 64, &sorted, 0));
+  BWTM_CUDA(cudaMemcpy(out_sorted, sorted, emitted * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  *n_values = emitted;
+  return BWTM_OK;
+}
+
+} // extern "C"

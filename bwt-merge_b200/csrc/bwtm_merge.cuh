@@ -1,0 +1,68 @@
+// Internal interfaces between the stages of the merge (K1 walk, K2 sort, K4 interleave, K5 encode).
+#pragma once
+
+#include "bwtm_internal.cuh"
+
+namespace bwtm
+{
+
+// K1. Appends one RA value per suffix of the sequences [seq_first, seq_last] of b to d_out (unordered).
+template<class KeyT>
+int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                   KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream);
+
+// K2. Radix sort on the low `bits` bits; *sorted points into d_keys or d_alt.
+template<class KeyT>
+int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream);
+
+// Sequential state of the byte encoder that crosses slabs (and GPU slices).
+struct EncodeControl
+{
+  unsigned long long out_size;      // bytes written so far (the `array.size()` of Run::write, support.h:267)
+  unsigned long long slab_base;     // out_size at the start of the slab's parallel part
+  unsigned long long carry_len;     // pending maximal run not yet written (RunBuffer state, utils.h:121-142)
+  unsigned int       carry_sym;
+  unsigned int       start;         // first run of the slab encoded by the parallel part
+  unsigned long long count;         // number of runs encoded by the parallel part
+  unsigned long long n_short;       // of which shorter than MAX_RUN
+  unsigned long long n_long;
+  unsigned long long long_bytes;    // bytes produced by the long runs of the slab
+  unsigned long long runs_total;    // maximal runs emitted so far
+};
+
+// K4 + K3 + K5 over the merged positions [begin, end): symbols of a and b interleaved according to
+// the sorted RA values `keys` (keys[j - key_base] is the RA value of b's position j), run detection
+// and the byte-exact writer.  Appends to *d_out (grown when needed); the encoder state lives in
+// d_control (device) and crosses calls.  `finish` flushes the pending run.
+struct OutputBuffer
+{
+  uint8_t* ptr;
+  uint64_t capacity;
+};
+
+// K3 + K5 on a stream of symbol slabs: run detection and the byte-exact Run::write.
+struct SlabEncoder
+{
+  uint64_t max_symbols;
+  DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, cub_temp;
+  int init(uint64_t max_symbols, cudaStream_t stream);
+  int encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
+  int finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
+};
+
+uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total);
+int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cudaStream_t stream);
+
+// Symbols of a complete sequence (device, one comp per byte) -> index. Used by the fixture builder.
+int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out);
+
+int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+                bwtm_index** result, bwtm_timings* timings);
+
+template<class KeyT>
+int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
+                     uint64_t begin, uint64_t end, uint64_t slab_symbols,
+                     OutputBuffer* out, EncodeControl* d_control, bool finish,
+                     float* interleave_ms, float* encode_ms, cudaStream_t stream);
+
+} // namespace bwtm

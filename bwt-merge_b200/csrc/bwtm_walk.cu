@@ -1,0 +1,187 @@
+// K1: the rank-array search, and K2: its radix sort.
+//
+// Replaces buildRA (fmi.cpp:272-334).  The reference walks the reverse trie of B depth first and
+// emits (rank in A, number of suffixes) per trie node; 87-96 % of its nodes are singletons
+// (SURVEY.md section 0), so the device does what the reference does for a singleton node
+// (fmi.cpp:296-303) for every suffix: one walker per sequence of B steps backwards with
+//     (c, b') = LF_B(b)          FMI::LF(i),    fmi.h:147-150  -> BWT::inverse_select, bwt.cpp:445-464
+//     a'      = LF_A(a, c)       FMI::LF(i, c), fmi.h:152-155  -> BWT::rank,           bwt.cpp:318-341
+// starting from (a, b) = (sequences of A, sequence id) (fmi.cpp:286) and emits `a` for every suffix.
+// The emitted multiset equals the reference's RA after run expansion.
+//
+// One thread = one walker; a warp refills finished lanes from a global sequence counter, so lanes
+// stay busy for any mix of sequence lengths.  Every step is two dependent 64-byte record reads
+// (B then A) at unrelated addresses: the kernel is bound by HBM random-sector throughput and hides
+// the latency with occupancy (>= 1024 resident walkers per SM).  RA values are staged per warp in
+// shared memory and appended to the output in coalesced chunks claimed with one atomic per chunk.
+#include <cub/cub.cuh>
+
+#include "bwtm_internal.cuh"
+#include "bwtm_merge.cuh"
+
+namespace bwtm
+{
+
+constexpr int WALK_THREADS = 256;
+constexpr int WALK_WARPS   = WALK_THREADS / 32;
+constexpr int WALK_STAGE   = 256;   // staged RA values per warp
+
+struct WalkCounters
+{
+  unsigned long long next_sequence;   // relative to seq_begin
+  unsigned long long emitted;
+  int                overflow;
+};
+
+template<class KeyT>
+__global__ void __launch_bounds__(WALK_THREADS, 4)
+k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
+        KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters)
+{
+  __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
+  __shared__ uint64_t c_a[8], c_b[8];
+
+  if(threadIdx.x < SIGMA + 1) { c_a[threadIdx.x] = a.C[threadIdx.x]; c_b[threadIdx.x] = b.C[threadIdx.x]; }
+  __syncthreads();
+
+  const unsigned FULL = 0xFFFFFFFFu;
+  const int lane = threadIdx.x & 31;
+  const unsigned lanes_below = (1u << lane) - 1u;
+  KeyT* stage = stage_all[threadIdx.x >> 5];
+
+  uint32_t fill = 0;          // warp-uniform
+  bool exhausted = false;     // warp-uniform
+  bool alive = false;
+  uint64_t pos_a = 0, pos_b = 0;
+
+  while(true)
+  {
+    // Refill finished lanes with new sequences.
+    unsigned need = __ballot_sync(FULL, !alive);
+    if(need != 0 && !exhausted)
+    {
+      unsigned long long base = 0;
+      int wanted = __popc(need);
+      if(lane == 0) { base = atomicAdd(&(counters->next_sequence), (unsigned long long)wanted); }
+      base = __shfl_sync(FULL, base, 0);
+      uint64_t first = seq_begin + base;
+      if(!alive)
+      {
+        uint64_t mine = first + __popc(need & lanes_below);
+        if(mine < seq_end) { alive = true; pos_b = mine; pos_a = a.sequences; }
+      }
+      if(first + wanted >= seq_end) { exhausted = true; }
+    }
+
+    unsigned active = __ballot_sync(FULL, alive);
+    if(active == 0) { break; }
+
+    // Emit the rank of the current suffix (fmi.cpp:290 with a run of length 1).
+    if(alive) { stage[fill + __popc(active & lanes_below)] = (KeyT)pos_a; }
+    fill += __popc(active);
+    if(fill > WALK_STAGE - 32)
+    {
+      __syncwarp();
+      unsigned long long base = 0;
+      if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+      base = __shfl_sync(FULL, base, 0);
+      if(base + fill <= capacity)
+      {
+        for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+      }
+      else
+      {
+        // More values than |B|: the input is not a valid BWT (or the buffer is too small). Stop this warp.
+        if(lane == 0) { counters->overflow = 1; }
+        alive = false; exhausted = true;
+      }
+      __syncwarp();
+      fill = 0;
+    }
+
+    // One backward step.
+    if(alive)
+    {
+      uint64_t record = pos_b >> RECORD_SHIFT;
+      Record rb = load_record(b, record);
+      uint32_t offset = (uint32_t)(pos_b & (RECORD_SYMBOLS - 1));
+      uint32_t comp = record_symbol(rb, offset);
+      if(comp == 0) { alive = false; }
+      else
+      {
+        pos_b = c_b[comp] + record_base(b, rb, record, comp) + record_rank(rb, offset, comp);
+        uint64_t record_a = pos_a >> RECORD_SHIFT;
+        Record ra = load_record(a, record_a);
+        pos_a = c_a[comp] + record_base(a, ra, record_a, comp)
+              + record_rank(ra, (uint32_t)(pos_a & (RECORD_SYMBOLS - 1)), comp);
+      }
+    }
+  }
+
+  if(fill > 0)
+  {
+    __syncwarp();
+    unsigned long long base = 0;
+    if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+    base = __shfl_sync(FULL, base, 0);
+    if(base + fill <= capacity)
+    {
+      for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+    }
+    else if(lane == 0) { counters->overflow = 1; }
+  }
+}
+
+template<class KeyT>
+int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                   KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream)
+{
+  DeviceBuffer counters; BWTM_TRY(counters.allocate(sizeof(WalkCounters)));
+  BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, sizeof(WalkCounters), stream));
+
+  int device = 0, sms = 0, per_sm = 0;
+  BWTM_CUDA(cudaGetDevice(&device));
+  BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk<KeyT>, WALK_THREADS, 0));
+  if(per_sm < 1) { per_sm = 1; }
+  uint64_t sequences = seq_last + 1 - seq_first;
+  uint64_t blocks = (uint64_t)sms * per_sm;
+  uint64_t needed = div_up(sequences, WALK_THREADS);
+  if(blocks > needed) { blocks = needed; }
+
+  k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
+    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
+  BWTM_LAUNCH_CHECK();
+
+  WalkCounters host;
+  BWTM_CUDA(cudaMemcpyAsync(&host, counters.ptr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  *emitted = host.emitted;
+  if(host.overflow) { set_error("rank array buffer too small: %llu values for capacity %llu",
+                                (unsigned long long)host.emitted, (unsigned long long)capacity); return BWTM_ERR_CAPACITY; }
+  return BWTM_OK;
+}
+
+template int walk_sequences<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, uint64_t*, cudaStream_t);
+template int walk_sequences<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, uint64_t*, cudaStream_t);
+
+// K2: sort of the RA values (support.h:421 sequentialSort + the merge cascade fmi.cpp:220-257).
+// Only the low `bits` bits are sorted.  The result is in `d_keys` or `d_alt`; returns which.
+template<class KeyT>
+int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream)
+{
+  cub::DoubleBuffer<KeyT> buffers(d_keys, d_alt);
+  size_t temp_bytes = 0;
+  BWTM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, buffers, (int64_t)n, 0, bits, stream));
+  DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
+  BWTM_CUDA(cub::DeviceRadixSort::SortKeys(temp.ptr, temp_bytes, buffers, (int64_t)n, 0, bits, stream));
+  count_launch((uint64_t)(2 + (bits + 7) / 8));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  *sorted = buffers.Current();
+  return BWTM_OK;
+}
+
+template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t);
+template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t);
+
+} // namespace bwtm
