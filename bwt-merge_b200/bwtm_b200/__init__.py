@@ -25,7 +25,7 @@ ERROR_NAMES = {-1: "BWTM_ERR_ARGUMENT", -2: "BWTM_ERR_CUDA", -3: "BWTM_ERR_MEMOR
 # Every symbol include/bwtm.h declares.
 EXPORTS = [
     "bwtm_last_error", "bwtm_version", "bwtm_device_count", "bwtm_set_device", "bwtm_kernel_launches",
-    "bwtm_index_create", "bwtm_index_create_device", "bwtm_index_destroy", "bwtm_index_get_info",
+    "bwtm_index_create", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_destroy", "bwtm_index_get_info",
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
     "bwtm_rank", "bwtm_lf", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
     "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
@@ -94,6 +94,7 @@ def lib():
     L.bwtm_kernel_launches.restype = C.c_uint64
     L.bwtm_index_create.argtypes = [u8p, C.c_uint64, u64p, C.POINTER(vp)]
     L.bwtm_index_create_device.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
+    L.bwtm_index_create_plain.argtypes = [u8p, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.bwtm_index_destroy.argtypes = [vp]
     L.bwtm_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.bwtm_index_download.argtypes = [vp, u8p, C.c_uint64, u64p]
@@ -183,6 +184,14 @@ class FMI:
         if expected_counts is not None:
             exp = _p(np.ascontiguousarray(expected_counts, dtype=np.uint64), u64p)
         check(lib().bwtm_index_create(_p(rle, u8p), len(rle), exp, C.byref(h)))
+        return cls(h)
+
+    @classmethod
+    def from_comps(cls, comps, slab_symbols=0):
+        """From a plain comp sequence (PlainData::read, formats.cpp:133-161): device run detection + Run::write."""
+        comps = np.ascontiguousarray(comps, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().bwtm_index_create_plain(_p(comps, u8p), len(comps), slab_symbols, C.byref(h)))
         return cls(h)
 
     @classmethod

@@ -687,6 +687,20 @@ int bwtm_merge(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options, 
   return rc;
 }
 
+int bwtm_index_create_plain(const uint8_t* comps, uint64_t n, uint64_t slab_symbols, bwtm_index** out)
+{
+  if(comps == nullptr || out == nullptr || n == 0) { set_error("null or empty argument"); return BWTM_ERR_ARGUMENT; }
+  *out = nullptr;
+  int count = 0;
+  if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+  {
+    cudaGetLastError(); set_error("no CUDA device available; this library has no CPU fallback"); return BWTM_ERR_CUDA;
+  }
+  DeviceBuffer symbols; BWTM_TRY(symbols.allocate(n));
+  BWTM_CUDA(cudaMemcpy(symbols.ptr, comps, n, cudaMemcpyHostToDevice));
+  return index_from_symbols(symbols.as<uint8_t>(), n, slab_symbols, 0, out);
+}
+
 int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                     uint64_t* out_sorted, uint64_t capacity, uint64_t* n_values)
 {

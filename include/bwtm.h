@@ -118,6 +118,10 @@ int bwtm_index_create(const uint8_t* rle, uint64_t rle_bytes, const uint64_t* ex
                       bwtm_index** out);
 /* Same, from RLE bytes that already live in device memory (copied). */
 int bwtm_index_create_device(const void* rle_device, uint64_t rle_bytes, bwtm_index** out);
+/* From a plain symbol sequence (one comp value per byte): the device counterpart of PlainData::read
+   (formats.cpp:133-161): maximal runs (RunBuffer) -> Run::write -> samples. `slab_symbols` = symbols
+   encoded per pass (0 = default). */
+int bwtm_index_create_plain(const uint8_t* comps, uint64_t n, uint64_t slab_symbols, bwtm_index** out);
 int bwtm_index_destroy(bwtm_index* index);
 int bwtm_index_get_info(const bwtm_index* index, bwtm_index_info* info);
 /* Copies the RLE bytes to the host (what BlockArray::serialize, support.cpp:296-309, writes after

@@ -278,6 +278,9 @@ class RefHooks:
         L.ref_samples.argtypes = [vp, u64p, u64p]
         L.ref_find.argtypes = [vp, C.c_char_p, C.c_uint64, u64p, u64p]
         L.ref_merge.restype = vp; L.ref_merge.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_char_p]
+        L.ref_fmi_copy.restype = vp; L.ref_fmi_copy.argtypes = [vp]
+        L.ref_merge_params.restype = vp
+        L.ref_merge_params.argtypes = [vp, vp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64, C.c_char_p]
 
     def run_write(self, prefix, comp, length):
         buf = np.zeros(len(prefix) + 64, dtype=np.uint8)
@@ -301,6 +304,16 @@ class RefHooks:
 
     def merge(self, a, b, threads=2, sequence_blocks=4, temp_dir="/tmp"):
         return RefFMI(self, self.L.ref_merge(a.h, b.h, threads, sequence_blocks, temp_dir.encode()))
+
+
+    def merge_params(self, a, b, threads, sequence_blocks=0, run_buffer_mb=0, thread_buffer_mb=0, merge_buffers=0,
+                     temp_dir="/tmp"):
+        """FMI(a, b, MergeParameters) with the reference defaults unless overridden (0 = default)."""
+        return RefFMI(self, self.L.ref_merge_params(a.h, b.h, threads, sequence_blocks, run_buffer_mb,
+                                                    thread_buffer_mb, merge_buffers, temp_dir.encode()))
+
+    def copy(self, fmi):
+        return RefFMI(self, self.L.ref_fmi_copy(fmi.h))
 
 
 class RefFMI:

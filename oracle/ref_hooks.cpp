@@ -6,6 +6,7 @@
   Used only by tests/ to pin oracle/bwtm_oracle.c: every function below is a thin call
   into reference code (the class and member it calls is named), no algorithm lives here.
 */
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <string>
@@ -162,6 +163,25 @@ void* ref_merge(void* a, void* b, uint64_t threads, uint64_t sequence_blocks, co
   parameters.sanitize();
   FMI* result = new FMI(*static_cast<FMI*>(a), *static_cast<FMI*>(b), parameters);
   return result;
+}
+
+// FMI copy constructor (fmi.h:94): lets a benchmark merge the same inputs repeatedly.
+void* ref_fmi_copy(void* handle) { return new FMI(*static_cast<FMI*>(handle)); }
+
+// FMI::FMI(a, b, parameters) with explicit MergeParameters; 0 keeps the reference default (fmi.h:49-52).
+void* ref_merge_params(void* a, void* b, uint64_t threads, uint64_t sequence_blocks, uint64_t run_buffer_mb,
+                       uint64_t thread_buffer_mb, uint64_t merge_buffers, const char* temp_dir)
+{
+  MergeParameters parameters;
+  parameters.setT(threads);
+  parameters.setSB(sequence_blocks > 0 ? sequence_blocks : threads * MergeParameters::BLOCKS_PER_THREAD);
+  if(run_buffer_mb > 0) { parameters.setRB(run_buffer_mb); }
+  if(thread_buffer_mb > 0) { parameters.setTB(thread_buffer_mb); }
+  if(merge_buffers > 0) { parameters.setMB(merge_buffers); }
+  parameters.setTemp(temp_dir);
+  parameters.sanitize();
+  Parallel::max_threads = parameters.threads;   // bwt_merge.cpp:136-137
+  return new FMI(*static_cast<FMI*>(a), *static_cast<FMI*>(b), parameters);
 }
 
 } // extern "C"

@@ -122,28 +122,52 @@ def test_sequential_multi_merge(oracle):
     assert np.array_equal(dev.extract(), direct)
 
 
+def _coalesce(runs):
+    out = []
+    for comp, length in runs:
+        if out and out[-1][0] == comp:
+            out[-1] = (comp, out[-1][1] + length)
+        else:
+            out.append((comp, length))
+    return out
+
+
 def test_encoder_offsets_and_long_runs(oracle):
-    """Run::write edge cases through the device encoder: long runs at every block offset."""
+    """Run::write edge cases through the device encoder (K3 + K5): long runs of every length class at
+    arbitrary block offsets. Homopolymer reads give BWTs that are a few very long runs; mixing read
+    lengths of 41..130 moves them over all offsets."""
     rng = np.random.default_rng(11)
-    for trial in range(6):
+    for trial in range(3):   # oracle self-check: split runs decode back to the maximal runs
         runs = []
         for _ in range(400):
-            kind = rng.integers(0, 4)
-            length = int(rng.integers(1, 42)) if kind == 0 else int(rng.choice([42, 43, 83, 169, 170, 171, 300, 5000, 16425, 16426, 70000]))
+            length = int(rng.integers(1, 42)) if rng.integers(0, 4) == 0 else int(rng.choice([42, 43, 83, 169, 170, 171, 300, 5000, 16425, 16426, 70000]))
             comp = int(rng.integers(1, 5))
             if runs and runs[-1][0] == comp:
                 comp = comp % 4 + 1
             runs.append((comp, length))
-        # as reads: one read per run would change the BWT; instead encode through a merge whose result is known:
-        # A = the run sequence itself is not a BWT, so use the builder path on constant reads instead (below).
+        assert _coalesce(oracle.decode_runs(oracle.encode_runs(runs))) == runs
+    for trial in range(8):
+        runs = []
+        for _ in range(int(rng.integers(1, 700))):
+            length = int(rng.integers(1, 42)) if rng.integers(0, 3) else int(rng.choice([42, 43, 82, 83, 84, 169, 170, 171, 300, 5000, 16425, 16426, 40000]))
+            comp = int(rng.integers(0, 6))
+            if runs and runs[-1][0] == comp:
+                comp = (comp + 1) % 6
+            runs.append((comp, length))
+        comps = np.repeat(np.array([r[0] for r in runs], np.uint8), [r[1] for r in runs])
         want = oracle.encode_runs(runs)
-        assert oracle.decode_runs(want) == runs
-    # homopolymer reads: BWT = m x 'A' ... long runs of every length class, built by the device builder + encoder
-    for m, L in ((50, 41), (97, 64), (300, 100)):
-        reads = np.full((m, L), 1, dtype=np.uint8)
-        D = FMI.from_reads(reads)
-        want = oracle.from_comps(oracle.bwt_of_reads([r for r in reads]))
-        assert np.array_equal(D.rle(), want.rle())
+        for slab in (0, 4096, 12288):
+            D = FMI.from_comps(comps, slab_symbols=slab)
+            assert np.array_equal(D.rle(), want), (trial, slab)
+            assert np.array_equal(D.counts(), np.bincount(comps, minlength=6).astype(np.uint64))
+    assert np.array_equal(FMI.from_comps(np.full(100000, 3, np.uint8), slab_symbols=4096).rle(), oracle.encode_runs([(3, 100000)]))
+    for m, L in ((50, 41), (97, 64), (300, 100), (1000, 130), (43, 42), (20000, 3)):
+        for base in (1, 4):
+            reads = np.full((m, L), base, dtype=np.uint8)
+            reads[m // 2:, L // 2:] = 2          # two read types: runs of several lengths
+            D = FMI.from_reads(reads)
+            want = oracle.from_comps(oracle.bwt_of_reads([r for r in reads]))
+            assert np.array_equal(D.rle(), want.rle()), (m, L, base)
 
 
 @pytest.mark.parametrize("shape", ["reads", "noisy_N", "repeats"])
