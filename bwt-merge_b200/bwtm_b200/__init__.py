@@ -29,7 +29,7 @@ EXPORTS = [
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
     "bwtm_rank", "bwtm_lf", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
     "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
-    "bwtm_tools_build_synthetic", "bwtm_tools_build_from_reads", "bwtm_tools_gather_bench",
+    "bwtm_tools_build_synthetic", "bwtm_tools_build_from_reads", "bwtm_tools_gather_bench", "bwtm_tools_chase_bench",
 ]
 
 
@@ -114,6 +114,7 @@ def lib():
                                              C.c_uint64, C.POINTER(vp)]
     L.bwtm_tools_build_from_reads.argtypes = [u8p, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.bwtm_tools_gather_bench.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_int, C.POINTER(C.c_double)]
+    L.bwtm_tools_chase_bench.argtypes = [C.c_uint64, C.c_uint32, C.c_uint64, C.c_uint32, C.c_uint32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -319,6 +320,13 @@ def rank_array(a, b, seq_first=0, seq_last=None):
 def gather_bench(table_bytes, granule, n_loads, iterations=3):
     g = C.c_double(0)
     check(lib().bwtm_tools_gather_bench(table_bytes, granule, n_loads, iterations, C.byref(g)))
+    return g.value
+
+
+def chase_bench(table_bytes, granule, n_loads, threads_per_sm=1024, l2_fetch_granularity=0):
+    """GB/s of dependent random loads of `granule` bytes: the rank/LF kernel's access pattern."""
+    g = C.c_double(0)
+    check(lib().bwtm_tools_chase_bench(table_bytes, granule, n_loads, threads_per_sm, l2_fetch_granularity, C.byref(g)))
     return g.value
 
 

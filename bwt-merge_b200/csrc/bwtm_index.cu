@@ -43,25 +43,55 @@ int cuda_failed(cudaError_t err, const char* what, const char* file, int line)
 
 void count_launch(uint64_t n) { launch_counter()->fetch_add(n); }
 
-int DeviceBuffer::allocate(uint64_t n)
+// All device memory comes from the device's default stream-ordered pool with an unlimited release
+// threshold: buffers freed by one merge are reused by the next one instead of going back to the driver
+// (cudaMalloc/cudaFree of the multi-GB work buffers cost more than the kernels they serve).
+static int configure_pool()
 {
-  this->release();
+  static thread_local int configured_device = -1;
+  int device = 0;
+  BWTM_CUDA(cudaGetDevice(&device));
+  if(device == configured_device) { return BWTM_OK; }
+  cudaMemPool_t pool;
+  BWTM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t threshold = UINT64_MAX;
+  BWTM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold));
+  configured_device = device;
+  return BWTM_OK;
+}
+
+int device_alloc(void** ptr, uint64_t n)
+{
+  *ptr = nullptr;
   if(n == 0) { n = 16; }
-  cudaError_t err = cudaMalloc(&(this->ptr), n);
+  BWTM_TRY(configure_pool());
+  cudaError_t err = cudaMallocAsync(ptr, n, 0);
   if(err != cudaSuccess)
   {
-    this->ptr = nullptr;
-    set_error("cudaMalloc of %llu bytes failed: %s", (unsigned long long)n, cudaGetErrorString(err));
+    *ptr = nullptr;
+    set_error("device allocation of %llu bytes failed: %s", (unsigned long long)n, cudaGetErrorString(err));
     cudaGetLastError();
     return BWTM_ERR_MEMORY;
   }
-  this->bytes = n;
+  return BWTM_OK;
+}
+
+void device_free(void* ptr)
+{
+  if(ptr != nullptr) { cudaFreeAsync(ptr, 0); }
+}
+
+int DeviceBuffer::allocate(uint64_t n)
+{
+  this->release();
+  BWTM_TRY(device_alloc(&(this->ptr), n));
+  this->bytes = (n == 0 ? 16 : n);
   return BWTM_OK;
 }
 
 void DeviceBuffer::release()
 {
-  if(this->ptr != nullptr) { cudaFree(this->ptr); this->ptr = nullptr; this->bytes = 0; }
+  if(this->ptr != nullptr) { device_free(this->ptr); this->ptr = nullptr; this->bytes = 0; }
 }
 
 //------------------------------------------------------------------------------
@@ -244,9 +274,9 @@ int rle_block_starts(const uint8_t* d_rle, uint64_t rle_bytes, uint64_t* d_start
 void index_free(bwtm_index* index)
 {
   if(index == nullptr) { return; }
-  if(index->d_rle != nullptr) { cudaFree(index->d_rle); }
-  if(index->d_records != nullptr) { cudaFree(index->d_records); }
-  if(index->d_super != nullptr) { cudaFree(index->d_super); }
+  device_free(index->d_rle);
+  device_free(index->d_records);
+  device_free(index->d_super);
   delete index;
 }
 

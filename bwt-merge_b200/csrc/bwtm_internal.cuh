@@ -36,7 +36,11 @@ inline DeviceIndex device_view(const bwtm_index* index)
   return v;
 }
 
-// RAII device buffer (cudaMalloc / cudaFree).
+// Stream-ordered pool allocation (bwtm_index.cu).
+int device_alloc(void** ptr, uint64_t bytes);
+void device_free(void* ptr);
+
+// RAII device buffer on the pool.
 struct DeviceBuffer
 {
   void*    ptr;

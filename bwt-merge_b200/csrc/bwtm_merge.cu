@@ -316,7 +316,7 @@ int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cu
     BWTM_CUDA(cudaMemcpyAsync(bigger.ptr, out->ptr, valid_bytes, cudaMemcpyDeviceToDevice, stream));
     BWTM_CUDA(cudaStreamSynchronize(stream));
   }
-  if(out->ptr != nullptr) { cudaFree(out->ptr); }
+  device_free(out->ptr);
   out->ptr = static_cast<uint8_t*>(bigger.detach());
   out->capacity = capacity;
   return BWTM_OK;
@@ -517,7 +517,7 @@ static int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* c
   BWTM_CUDA(cudaMemcpyAsync(exact.ptr, out->ptr, rle_bytes, cudaMemcpyDeviceToDevice, stream));
   BWTM_CUDA(cudaMemsetAsync(exact.as<uint8_t>() + rle_bytes, 0, RLE_PADDING, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  cudaFree(out->ptr); out->ptr = nullptr; out->capacity = 0;
+  device_free(out->ptr); out->ptr = nullptr; out->capacity = 0;
 
   if(!skip_index)
   {
@@ -570,7 +570,7 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
     set_error("cannot read the encoder state"); rc = BWTM_ERR_CUDA;
   }
   if(rc == BWTM_OK) { rc = finish_index(&buffer, ctl.out_size, nullptr, 0, false, stream, out); }
-  if(buffer.ptr != nullptr) { cudaFree(buffer.ptr); }
+  device_free(buffer.ptr);
   return rc;
 }
 
@@ -625,7 +625,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
     rc = interleave_range<KeyT>(a, b, sorted, 0, n_b, 0, a->size + b->size, options->slab_symbols,
                                 &out, control.as<EncodeControl>(), true, &interleave_ms, &encode_ms, stream);
   }
-  if(rc != BWTM_OK) { if(out.ptr != nullptr) { cudaFree(out.ptr); } return rc; }
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   timings->interleave_seconds = interleave_ms * 1e-3;
   timings->encode_seconds = encode_ms * 1e-3;
   keys.release(); alt.release();
@@ -639,7 +639,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   uint64_t counts[SIGMA];
   for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
   rc = finish_index(&out, ctl.out_size, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
-  if(out.ptr != nullptr) { cudaFree(out.ptr); }
+  device_free(out.ptr);
   timings->index_seconds = timer.stop() * 1e-3;
   return rc;
 }

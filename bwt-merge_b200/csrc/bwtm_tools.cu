@@ -148,20 +148,54 @@ static int build_dispatch(const uint8_t* d_reads, uint64_t reads, uint64_t read_
 // Random-access microbenchmark
 
 template<int GRANULE>
-__global__ void gather_kernel(const uint4* __restrict__ table, uint64_t granules, uint64_t loads_per_thread, uint64_t seed,
-                              uint32_t* __restrict__ sink)
+__global__ void __launch_bounds__(256)
+gather_kernel(const uint4* __restrict__ table, uint64_t granules, uint64_t loads_per_thread, uint64_t seed,
+              uint32_t* __restrict__ sink)
 {
   uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   uint64_t state = mix64(seed + tid);
   uint32_t acc = 0;
   constexpr int VEC = GRANULE / 16;
-  for(uint64_t k = 0; k < loads_per_thread; k++)
+  constexpr int BATCH = (GRANULE == 128 ? 2 : 4);   // independent granules in flight per thread
+  for(uint64_t k = 0; k < loads_per_thread; k += BATCH)
   {
-    state = state * 6364136223846793005ull + 1442695040888963407ull;
-    uint64_t g = (state >> 16) % granules;
-    const uint4* p = table + g * VEC;
+    uint4 q[BATCH][VEC];
 #pragma unroll
-    for(int v = 0; v < VEC; v++) { uint4 q = __ldg(p + v); acc ^= q.x ^ q.y ^ q.z ^ q.w; }
+    for(int b = 0; b < BATCH; b++)
+    {
+      state = state * 6364136223846793005ull + 1442695040888963407ull;
+      uint64_t g = __umul64hi(state, granules);     // uniform in [0, granules)
+      const uint4* p = table + g * VEC;
+#pragma unroll
+      for(int v = 0; v < VEC; v++) { q[b][v] = __ldg(p + v); }
+    }
+#pragma unroll
+    for(int b = 0; b < BATCH; b++)
+    {
+#pragma unroll
+      for(int v = 0; v < VEC; v++) { acc ^= q[b][v].x ^ q[b][v].y ^ q[b][v].z ^ q[b][v].w; }
+    }
+  }
+  if(acc == 0x12345678u) { sink[0] = acc; }
+}
+
+template<int GRANULE>
+__global__ void __launch_bounds__(256)
+chase_kernel(const uint4* __restrict__ table, uint64_t granules, uint64_t steps, uint64_t seed, uint32_t* __restrict__ sink)
+{
+  uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t state = mix64(seed + tid);
+  uint32_t acc = 0;
+  constexpr int VEC = GRANULE / 16;
+  for(uint64_t k = 0; k < steps; k++)
+  {
+    uint64_t g = __umul64hi(state, granules);
+    const uint4* p = table + g * VEC;
+    uint32_t x = 0;
+#pragma unroll
+    for(int v = 0; v < VEC; v++) { uint4 q = __ldg(p + v); x ^= q.x ^ q.y ^ q.z ^ q.w; }
+    acc ^= x;
+    state = state * 6364136223846793005ull + 1442695040888963407ull + x;   // the next address depends on the data
   }
   if(acc == 0x12345678u) { sink[0] = acc; }
 }
@@ -229,7 +263,7 @@ int bwtm_tools_gather_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_l
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   uint64_t threads = (uint64_t)sms * 2048;
-  uint64_t per_thread = std::max<uint64_t>(1, n_loads / threads);
+  uint64_t per_thread = std::max<uint64_t>(4, (n_loads / threads) & ~3ull);
   uint64_t granules = table_bytes / granule;
   cudaEvent_t begin, end;
   BWTM_CUDA(cudaEventCreate(&begin)); BWTM_CUDA(cudaEventCreate(&end));
@@ -247,6 +281,48 @@ int bwtm_tools_gather_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_l
     float ms = 0.0f; BWTM_CUDA(cudaEventElapsedTime(&ms, begin, end));
     double gbs = (double)(threads * per_thread) * granule / (ms * 1e-3) / 1e9;
     if(it > 0 && gbs > best) { best = gbs; }   // iteration 0 is the warm-up
+  }
+  cudaEventDestroy(begin); cudaEventDestroy(end);
+  *gbytes_per_second = best;
+  return BWTM_OK;
+}
+
+int bwtm_tools_chase_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_loads, uint32_t threads_per_sm,
+                           uint32_t l2_fetch_granularity, double* gbytes_per_second)
+{
+  if(gbytes_per_second == nullptr || (granule != 32 && granule != 64 && granule != 128) || table_bytes < 4096 ||
+     threads_per_sm == 0 || threads_per_sm % 256 != 0 || threads_per_sm > 2048)
+  {
+    set_error("invalid argument"); return BWTM_ERR_ARGUMENT;
+  }
+  int count = 0;
+  if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0) { cudaGetLastError(); set_error("no CUDA device available"); return BWTM_ERR_CUDA; }
+  if(l2_fetch_granularity != 0) { BWTM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, l2_fetch_granularity)); }
+  DeviceBuffer table, sink;
+  BWTM_TRY(table.allocate(table_bytes)); BWTM_TRY(sink.allocate(16));
+  BWTM_CUDA(cudaMemset(table.ptr, 1, table_bytes));
+  int device = 0, sms = 0;
+  BWTM_CUDA(cudaGetDevice(&device));
+  BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  uint64_t threads = (uint64_t)sms * threads_per_sm;
+  uint64_t steps = std::max<uint64_t>(1, n_loads / threads);
+  uint64_t granules = table_bytes / granule;
+  unsigned grid = (unsigned)(threads / 256);
+  cudaEvent_t begin, end;
+  BWTM_CUDA(cudaEventCreate(&begin)); BWTM_CUDA(cudaEventCreate(&end));
+  double best = 0.0;
+  for(int it = 0; it < 3; it++)
+  {
+    BWTM_CUDA(cudaEventRecord(begin));
+    if(granule == 32)       { chase_kernel<32><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
+    else if(granule == 64)  { chase_kernel<64><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
+    else                    { chase_kernel<128><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
+    BWTM_LAUNCH_CHECK();
+    BWTM_CUDA(cudaEventRecord(end));
+    BWTM_CUDA(cudaEventSynchronize(end));
+    float ms = 0.0f; BWTM_CUDA(cudaEventElapsedTime(&ms, begin, end));
+    double gbs = (double)(threads * steps) * granule / (ms * 1e-3) / 1e9;
+    if(it > 0 && gbs > best) { best = gbs; }
   }
   cudaEventDestroy(begin); cudaEventDestroy(end);
   *gbytes_per_second = best;

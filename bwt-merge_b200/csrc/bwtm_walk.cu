@@ -139,6 +139,13 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
   DeviceBuffer counters; BWTM_TRY(counters.allocate(sizeof(WalkCounters)));
   BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, sizeof(WalkCounters), stream));
 
+  if(const char* fetch = getenv("BWTM_L2_FETCH"))   // experiment knob: cudaLimitMaxL2FetchGranularity (32/64/128)
+  {
+    size_t before = 0; cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+    BWTM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fetch)));
+    size_t after = 0; cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+    if(getenv("BWTM_DEBUG")) { fprintf(stderr, "bwtm: L2 fetch granularity %zu -> %zu\n", before, after); }
+  }
   int device = 0, sms = 0, per_sm = 0;
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
