@@ -14,6 +14,9 @@
 // (B then A) at unrelated addresses: the kernel is bound by HBM random-sector throughput and hides
 // the latency with occupancy (>= 1024 resident walkers per SM).  RA values are staged per warp in
 // shared memory and appended to the output in coalesced chunks claimed with one atomic per chunk.
+#include <algorithm>
+#include <cstdlib>
+
 #include <cub/cub.cuh>
 
 #include "bwtm_internal.cuh"
@@ -41,7 +44,8 @@ k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
   __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
   __shared__ uint64_t c_a[8], c_b[8];
 
-  if(threadIdx.x < SIGMA + 1) { c_a[threadIdx.x] = a.C[threadIdx.x]; c_b[threadIdx.x] = b.C[threadIdx.x]; }
+#pragma unroll
+  for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = a.C[c]; c_b[c] = b.C[c]; } }
   __syncthreads();
 
   const unsigned FULL = 0xFFFFFFFFu;
@@ -132,6 +136,145 @@ k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
   }
 }
 
+// K1, cooperative form.  Measured on B200 (profiles/r01_random_line_ceiling_coop_chase.txt): dependent random
+// reads are limited by the number of 128-byte LINE REQUESTS, about 39.4 G lines/s, whatever the record size
+// (32, 64 or 128 bytes), and a record read by four consecutive 16-byte loads of one thread costs two
+// requests.  So four lanes share one walker: lane `sub` loads chunk `sub` of the record, the whole 64-byte
+// record is one instruction and one line request, the in-record rank is a popcount per lane plus two
+// shuffles, and the header counter is fetched from the lanes that hold its words.  Loads carry the
+// L2::64B hint: without it every record miss fetched a full 128-byte line from HBM (346 GB of DRAM reads
+// for 193 GB of records, profiles/r01_k1_walk_v1_ncu_raw.csv).
+constexpr int COOP_LANES = 4;
+
+__device__ __forceinline__ uint4 load_chunk_64B(const uint4* p)
+{
+  uint4 r;
+  asm volatile("ld.global.nc.L2::64B.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
+// One LF / rank step of a 4-lane group on `idx` at position `pos` for comp `comp` (1..5):
+// returns C-less rank = (count before the record) + (count inside the record before pos).
+__device__ __forceinline__ uint64_t coop_rank(const DeviceIndex& idx, const uint4& q, uint64_t pos, uint32_t comp,
+                                              unsigned mask, int sub, int group_base)
+{
+  uint32_t offset = (uint32_t)(pos & (RECORD_SYMBOLS - 1));
+  int k = (int)offset - 32 * sub;
+  k = (k < 0 ? 0 : k);
+  uint32_t count = __popc(match_mask(q, comp) & low_mask(k));
+  count += __shfl_xor_sync(mask, count, 1);
+  count += __shfl_xor_sync(mask, count, 2);
+  uint32_t s = 25u * ((comp - 1u) & 7u);
+  uint32_t w = s >> 5, shift = s & 31u;
+  uint32_t lo = __shfl_sync(mask, q.w, group_base + (int)w);
+  uint32_t hi = __shfl_sync(mask, q.w, group_base + (int)(w < 3 ? w + 1 : 3));
+  uint32_t field = __funnelshift_r(lo, hi, shift) & FIELD_MASK;
+  uint64_t record = pos >> RECORD_SHIFT;
+  return __ldg(idx.super + (record >> SUPER_RECORD_SHIFT) * SUPER_STRIDE + comp) + field + count;
+}
+
+template<class KeyT>
+__global__ void __launch_bounds__(WALK_THREADS, 8)
+k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
+             KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters)
+{
+  __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
+  __shared__ uint64_t c_a[8], c_b[8];
+
+#pragma unroll
+  for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = a.C[c]; c_b[c] = b.C[c]; } }
+  __syncthreads();
+
+  const unsigned FULL = 0xFFFFFFFFu;
+  const unsigned LEADERS = 0x11111111u;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane & (COOP_LANES - 1);
+  const int group_base = lane & ~(COOP_LANES - 1);
+  const unsigned leaders_below = LEADERS & ((1u << group_base) - 1u);
+  KeyT* stage = stage_all[threadIdx.x >> 5];
+  const uint64_t first_rank = a.sequences;
+
+  uint32_t fill = 0;          // warp-uniform
+  bool exhausted = false;     // warp-uniform
+  bool alive = false;         // uniform within a group
+  uint64_t pos_a = 0, pos_b = 0;
+
+  while(true)
+  {
+    unsigned need = __ballot_sync(FULL, !alive) & LEADERS;
+    if(need != 0 && !exhausted)
+    {
+      unsigned long long base = 0;
+      int wanted = __popc(need);
+      if(lane == 0) { base = atomicAdd(&(counters->next_sequence), (unsigned long long)wanted); }
+      base = __shfl_sync(FULL, base, 0);
+      uint64_t first = seq_begin + base;
+      if(!alive)
+      {
+        uint64_t mine = first + __popc(need & leaders_below);
+        if(mine < seq_end) { alive = true; pos_b = mine; pos_a = first_rank; }
+      }
+      if(first + wanted >= seq_end) { exhausted = true; }
+    }
+
+    unsigned active = __ballot_sync(FULL, alive);
+    if(active == 0) { break; }
+
+    if(alive && sub == 0) { stage[fill + __popc(active & leaders_below)] = (KeyT)pos_a; }
+    fill += __popc(active & LEADERS);
+    if(fill > WALK_STAGE - 8)
+    {
+      __syncwarp();
+      unsigned long long base = 0;
+      if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+      base = __shfl_sync(FULL, base, 0);
+      if(base + fill <= capacity)
+      {
+        for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+      }
+      else
+      {
+        if(lane == 0) { counters->overflow = 1; }
+        alive = false; exhausted = true;
+      }
+      __syncwarp();
+      fill = 0;
+      active = __ballot_sync(FULL, alive);
+      if(active == 0) { break; }
+    }
+
+    if(alive)
+    {
+      // (c, b') = LF_B(b): FMI::LF(i), fmi.h:147-150
+      uint4 qb = load_chunk_64B(b.records + 4 * (pos_b >> RECORD_SHIFT) + sub);
+      uint32_t offset = (uint32_t)(pos_b & (RECORD_SYMBOLS - 1));
+      uint32_t t = offset & 31u;
+      uint32_t mine = ((qb.x >> t) & 1u) | (((qb.y >> t) & 1u) << 1) | (((qb.z >> t) & 1u) << 2);
+      uint32_t comp = __shfl_sync(active, mine, group_base + (int)(offset >> 5));
+      // a' = LF_A(a, c): FMI::LF(i, c), fmi.h:152-155. Issued before B's rank arithmetic: both records in flight.
+      uint4 qa = load_chunk_64B(a.records + 4 * (pos_a >> RECORD_SHIFT) + sub);
+      uint32_t safe = (comp == 0 ? 1u : comp);
+      uint64_t next_b = c_b[safe] + coop_rank(b, qb, pos_b, safe, active, sub, group_base);
+      uint64_t next_a = c_a[safe] + coop_rank(a, qa, pos_a, safe, active, sub, group_base);
+      if(comp == 0) { alive = false; }
+      else { pos_b = next_b; pos_a = next_a; }
+    }
+  }
+
+  if(fill > 0)
+  {
+    __syncwarp();
+    unsigned long long base = 0;
+    if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+    base = __shfl_sync(FULL, base, 0);
+    if(base + fill <= capacity)
+    {
+      for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+    }
+    else if(lane == 0) { counters->overflow = 1; }
+  }
+}
+
 template<class KeyT>
 int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                    KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream)
@@ -139,25 +282,27 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
   DeviceBuffer counters; BWTM_TRY(counters.allocate(sizeof(WalkCounters)));
   BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, sizeof(WalkCounters), stream));
 
-  if(const char* fetch = getenv("BWTM_L2_FETCH"))   // experiment knob: cudaLimitMaxL2FetchGranularity (32/64/128)
-  {
-    size_t before = 0; cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
-    BWTM_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fetch)));
-    size_t after = 0; cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
-    if(getenv("BWTM_DEBUG")) { fprintf(stderr, "bwtm: L2 fetch granularity %zu -> %zu\n", before, after); }
-  }
   int device = 0, sms = 0, per_sm = 0;
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk<KeyT>, WALK_THREADS, 0));
-  if(per_sm < 1) { per_sm = 1; }
   uint64_t sequences = seq_last + 1 - seq_first;
-  uint64_t blocks = (uint64_t)sms * per_sm;
-  uint64_t needed = div_up(sequences, WALK_THREADS);
-  if(blocks > needed) { blocks = needed; }
-
-  k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
-    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
+  const char* variant = getenv("BWTM_WALK");
+  if(variant != nullptr && variant[0] == '1')   // thread-per-walker form, kept for A/B measurements
+  {
+    BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk<KeyT>, WALK_THREADS, 0));
+    if(per_sm < 1) { per_sm = 1; }
+    uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS));
+    k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
+      device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
+  }
+  else
+  {
+    BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_coop<KeyT>, WALK_THREADS, 0));
+    if(per_sm < 1) { per_sm = 1; }
+    uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS / COOP_LANES));
+    k1_walk_coop<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
+      device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
+  }
   BWTM_LAUNCH_CHECK();
 
   WalkCounters host;
