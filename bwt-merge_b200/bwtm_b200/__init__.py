@@ -28,7 +28,7 @@ EXPORTS = [
     "bwtm_index_create", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_destroy", "bwtm_index_get_info",
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
     "bwtm_rank", "bwtm_lf", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
-    "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
+    "bwtm_shard_range", "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
     "bwtm_tools_build_synthetic", "bwtm_tools_build_from_reads", "bwtm_tools_gather_bench", "bwtm_tools_chase_bench",
 ]
 
@@ -106,6 +106,7 @@ def lib():
     L.bwtm_count.argtypes = [vp, u8p, u64p, C.c_uint64, u8p, u64p]
     L.bwtm_merge.argtypes = [vp, vp, C.POINTER(MergeOptions), C.POINTER(vp), C.POINTER(Timings)]
     L.bwtm_rank_array.argtypes = [vp, vp, C.c_uint64, C.c_uint64, u64p, C.c_uint64, u64p]
+    L.bwtm_shard_range.argtypes = [C.c_uint64, C.c_uint32, C.c_uint32, u64p, u64p]
     L.bwtm_comm_unique_id.argtypes = [u8p]
     L.bwtm_comm_create.argtypes = [u8p, C.c_int, C.c_int, C.POINTER(vp)]
     L.bwtm_comm_destroy.argtypes = [vp]
@@ -306,6 +307,69 @@ class FMI:
             c2c = _p(np.ascontiguousarray(char2comp, dtype=np.uint8), u8p)
         check(lib().bwtm_count(self._h, _p(flat, u8p), _p(offsets, u64p), len(arrays), c2c, _p(out, u64p)))
         return out
+
+
+def shard_range(total, rank, world):
+    """[first, first + count) of `total` sequence ids owned by `rank` (bwtm_shard_range)."""
+    first = C.c_uint64(0); count = C.c_uint64(0)
+    check(lib().bwtm_shard_range(total, rank, world, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+COMM_ID_BYTES = 128
+
+
+def comm_unique_id():
+    buf = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+    check(lib().bwtm_comm_unique_id(_p(buf, u8p)))
+    return buf
+
+
+class Communicator:
+    """One process per GPU (bwtm_comm): NCCL communicator owned by the library."""
+
+    def __init__(self, unique_id, rank, world):
+        unique_id = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        assert len(unique_id) == COMM_ID_BYTES
+        self._h = C.c_void_p()
+        self.rank, self.world = rank, world
+        check(lib().bwtm_comm_create(_p(unique_id, u8p), rank, world, C.byref(self._h)))
+
+    @classmethod
+    def from_torch(cls, dist, rank, world):
+        """Rank 0 creates the NCCL id; it is broadcast through the given torch.distributed module."""
+        import torch
+        ident = torch.zeros(COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            ident = torch.from_numpy(comm_unique_id().copy())
+        if dist.get_backend() == "nccl":
+            ident = ident.cuda(); dist.broadcast(ident, 0); ident = ident.cpu()
+        else:
+            dist.broadcast(ident, 0)
+        return cls(ident.numpy(), rank, world)
+
+    def merge(self, a, b, parameters=None, keep_inputs=False):
+        """bwtm_merge_distributed: collective; every rank returns the complete merged FMI."""
+        parameters = parameters or MergeParameters()
+        opts = parameters.to_c(keep_inputs)
+        out = C.c_void_p(); t = Timings()
+        ha, hb = a._h, b._h
+        if not keep_inputs:
+            a._h = None; b._h = None
+        check(lib().bwtm_merge_distributed(self._h, ha, hb, C.byref(opts), C.byref(out), C.byref(t)))
+        m = FMI(out); m.timings = t
+        return m
+
+    def close(self):
+        if self._h is not None and _lib is not None:
+            _lib.bwtm_comm_destroy(self._h)
+        self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def rank_array(a, b, seq_first=0, seq_last=None):

@@ -1,19 +1,429 @@
-// Multi-GPU merge.  Placeholder: the single-GPU path is brought up first.
+// Multi-GPU merge: one process per GPU, NCCL over NVLink.
+//
+//   search      : both indexes are replicated; rank r walks the sequences [m r / G, m (r + 1) / G) of B
+//                 (the reference's own unit of parallelism, fmi.cpp:355) and sorts its RA values locally;
+//   exchange    : G - 1 splitters on A positions are found by a distributed binary search so that every
+//                 rank gets the same number of MERGED positions; one all-to-all (grouped ncclSend/ncclRecv)
+//                 moves every RA value to the rank that owns its A-position range;
+//   interleave  : rank r owns A positions [s_r, s_{r+1}) and the B symbols whose RA value lies there: a
+//                 contiguous slice of the merged BWT. Symbols and maximal runs (K4, K3) are computed on all
+//                 ranks at once; the byte writer (K5) needs the output offset modulo 64 and the pending run
+//                 of the previous slice, so its 88-byte state travels down the ranks;
+//   gather      : slices are broadcast into the complete run-length BWT on every rank, which rebuilds its
+//                 replica of the rank structure (the next sequential merge needs it everywhere).
+//
+// There is no collective in the search itself. NCCL is loaded with dlopen so that single-GPU users do not
+// need it.
+#include <dlfcn.h>
+
+#include <algorithm>
+#include <cstring>
+#include <chrono>
+#include <vector>
+
+#include <nccl.h>
+
 #include "bwtm_merge.cuh"
 
 using namespace bwtm;
 
-struct bwtm_comm { int rank, world; };
+namespace
+{
+
+struct NcclApi
+{
+  void* handle = nullptr;
+  decltype(&ncclGetUniqueId)    GetUniqueId = nullptr;
+  decltype(&ncclCommInitRank)   CommInitRank = nullptr;
+  decltype(&ncclCommDestroy)    CommDestroy = nullptr;
+  decltype(&ncclAllGather)      AllGather = nullptr;
+  decltype(&ncclAllReduce)      AllReduce = nullptr;
+  decltype(&ncclBroadcast)      Broadcast = nullptr;
+  decltype(&ncclSend)           Send = nullptr;
+  decltype(&ncclRecv)           Recv = nullptr;
+  decltype(&ncclGroupStart)     GroupStart = nullptr;
+  decltype(&ncclGroupEnd)       GroupEnd = nullptr;
+  decltype(&ncclGetErrorString) GetErrorString = nullptr;
+  bool ok = false;
+};
+
+NcclApi* nccl()
+{
+  static NcclApi api;
+  static bool tried = false;
+  if(tried) { return &api; }
+  tried = true;
+  const char* names[] = { "libnccl.so.2", "libnccl.so" };
+  for(const char* name : names)
+  {
+    api.handle = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+    if(api.handle != nullptr) { break; }
+  }
+  if(api.handle == nullptr) { return &api; }
+#define BWTM_NCCL_SYM(field, symbol) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, symbol)); if(api.field == nullptr) { return &api; }
+  BWTM_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+  BWTM_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+  BWTM_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+  BWTM_NCCL_SYM(AllGather, "ncclAllGather")
+  BWTM_NCCL_SYM(AllReduce, "ncclAllReduce")
+  BWTM_NCCL_SYM(Broadcast, "ncclBroadcast")
+  BWTM_NCCL_SYM(Send, "ncclSend")
+  BWTM_NCCL_SYM(Recv, "ncclRecv")
+  BWTM_NCCL_SYM(GroupStart, "ncclGroupStart")
+  BWTM_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+  BWTM_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+#undef BWTM_NCCL_SYM
+  api.ok = true;
+  return &api;
+}
+
+int nccl_failed(ncclResult_t result, const char* what)
+{
+  set_error("NCCL error in %s: %s", what, nccl()->ok ? nccl()->GetErrorString(result) : "library not loaded");
+  return BWTM_ERR_COMM;
+}
+
+#define BWTM_NCCL(call) do { ncclResult_t res__ = (call); if(res__ != ncclSuccess) { return nccl_failed(res__, #call); } } while(0)
+
+} // namespace
+
+struct bwtm_comm
+{
+  ncclComm_t comm;
+  int        rank, world;
+};
+
+namespace bwtm
+{
+
+// First index with keys[index] >= probe, for each probe.
+template<class KeyT>
+__global__ void lower_bounds(const KeyT* __restrict__ keys, uint64_t n, const unsigned long long* __restrict__ probes, int n_probes,
+                             unsigned long long* __restrict__ out)
+{
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if(k >= n_probes) { return; }
+  unsigned long long probe = probes[k];
+  uint64_t lo = 0, hi = n;
+  while(lo < hi)
+  {
+    uint64_t mid = lo + (hi - lo) / 2;
+    if((unsigned long long)keys[mid] < probe) { lo = mid + 1; } else { hi = mid; }
+  }
+  out[k] = lo;
+}
+
+template<class KeyT> struct NcclKey;
+template<> struct NcclKey<uint32_t> { static constexpr ncclDataType_t type = ncclUint32; };
+template<> struct NcclKey<uint64_t> { static constexpr ncclDataType_t type = ncclUint64; };
+
+template<class KeyT>
+static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+                                  bwtm_index** result, bwtm_timings* timings)
+{
+  NcclApi* api = nccl();
+  cudaStream_t stream = 0;
+  const int G = comm->world, r = comm->rank;
+  const uint64_t n_a = a->size, n_b = b->size, m_b = b->sequences;
+  EventTimer timer(stream);
+
+  // 1. search + local sort
+  uint64_t seq_first = 0, seq_count = 0;
+  bwtm_shard_range(m_b, (uint32_t)r, (uint32_t)G, &seq_first, &seq_count);
+  uint64_t capacity = std::min<uint64_t>(n_b, (uint64_t)((double)n_b * ((double)seq_count / (double)m_b) * 1.25) + (1ull << 20));
+  DeviceBuffer keys, alt;
+  uint64_t local_n = 0;
+  timer.start();
+  for(int attempt = 0; attempt < 2; attempt++)
+  {
+    BWTM_TRY(keys.allocate(std::max<uint64_t>(capacity, 1) * sizeof(KeyT)));
+    if(seq_count == 0) { break; }
+    int rc = walk_sequences<KeyT>(a, b, seq_first, seq_first + seq_count - 1, keys.as<KeyT>(), capacity, &local_n, stream);
+    if(rc == BWTM_OK) { break; }
+    if(rc != BWTM_ERR_CAPACITY || attempt == 1 || capacity == n_b) { return rc; }
+    capacity = n_b;   // sequences of very different lengths: take the upper bound
+  }
+  timings->search_seconds = timer.stop() * 1e-3;
+  timings->walk_kernel_launches = (seq_count > 0 ? 1 : 0);
+
+  timer.start();
+  const int bits = bit_length_host(n_a);
+  KeyT* sorted = keys.as<KeyT>();
+  if(local_n > 0)
+  {
+    BWTM_TRY(alt.allocate(local_n * sizeof(KeyT)));
+    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), local_n, bits, &sorted, stream));
+  }
+  timings->sort_seconds = timer.stop() * 1e-3;
+
+  // 2. splitters: smallest p with p + #{keys < p} >= k (n_a + n_b) / G
+  timer.start();
+  auto exchange_start = std::chrono::steady_clock::now();
+  const int P = G - 1;
+  std::vector<unsigned long long> lo(std::max(P, 1), 0), hi(std::max(P, 1), n_a + 1), mid(std::max(P, 1), 0), below(std::max(P, 1), 0);
+  DeviceBuffer d_probes, d_counts;
+  BWTM_TRY(d_probes.allocate(std::max(P, 1) * sizeof(unsigned long long)));
+  BWTM_TRY(d_counts.allocate(std::max(P, 1) * sizeof(unsigned long long)));
+  std::vector<unsigned long long> target(std::max(P, 1), 0);
+  for(int k = 0; k < P; k++) { target[k] = (unsigned long long)(((__uint128_t)(n_a + n_b) * (k + 1)) / G); }
+  for(int iteration = 0; P > 0 && iteration < 66; iteration++)
+  {
+    bool open = false;
+    for(int k = 0; k < P; k++) { mid[k] = lo[k] + (hi[k] - lo[k]) / 2; open = open || (lo[k] < hi[k]); }
+    if(!open) { break; }
+    BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, mid.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    lower_bounds<KeyT><<<1, 32, 0, stream>>>(sorted, local_n, d_probes.as<unsigned long long>(), P, d_counts.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+    BWTM_NCCL(api->AllReduce(d_counts.ptr, d_counts.ptr, P, ncclUint64, ncclSum, comm->comm, stream));
+    BWTM_CUDA(cudaMemcpyAsync(below.data(), d_counts.ptr, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    for(int k = 0; k < P; k++)
+    {
+      if(lo[k] >= hi[k]) { continue; }
+      if(mid[k] + below[k] >= target[k]) { hi[k] = mid[k]; } else { lo[k] = mid[k] + 1; }
+    }
+  }
+  std::vector<unsigned long long> splitter(G + 1, 0);
+  for(int k = 0; k < P; k++) { splitter[k + 1] = std::max(lo[k], splitter[k]); }
+  splitter[G] = n_a + 1;
+
+  // 3. how many of my values go to each rank
+  std::vector<unsigned long long> send_offset(G + 1, 0);
+  if(P > 0)
+  {
+    BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, splitter.data() + 1, P * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    lower_bounds<KeyT><<<1, 32, 0, stream>>>(sorted, local_n, d_probes.as<unsigned long long>(), P, d_counts.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+    BWTM_CUDA(cudaMemcpyAsync(send_offset.data() + 1, d_counts.ptr, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+  }
+  send_offset[G] = local_n;
+  std::vector<unsigned long long> send_count(G, 0), matrix((size_t)G * G, 0);
+  for(int k = 0; k < G; k++) { send_count[k] = send_offset[k + 1] - send_offset[k]; }
+  DeviceBuffer d_send_count, d_matrix;
+  BWTM_TRY(d_send_count.allocate(G * sizeof(unsigned long long)));
+  BWTM_TRY(d_matrix.allocate((size_t)G * G * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemcpyAsync(d_send_count.ptr, send_count.data(), G * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  BWTM_NCCL(api->AllGather(d_send_count.ptr, d_matrix.ptr, G, ncclUint64, comm->comm, stream));
+  BWTM_CUDA(cudaMemcpyAsync(matrix.data(), d_matrix.ptr, (size_t)G * G * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+
+  uint64_t recv_total = 0, b_lo = 0, all_values = 0;
+  std::vector<uint64_t> recv_offset(G + 1, 0);
+  for(int src = 0; src < G; src++)
+  {
+    recv_offset[src + 1] = recv_offset[src] + matrix[(size_t)src * G + r];
+    for(int dst = 0; dst < G; dst++) { all_values += matrix[(size_t)src * G + dst]; if(dst < r) { b_lo += matrix[(size_t)src * G + dst]; } }
+  }
+  recv_total = recv_offset[G];
+  if(all_values != n_b)
+  {
+    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
+              (unsigned long long)all_values, (unsigned long long)n_b);
+    return BWTM_ERR_INTERNAL;
+  }
+  timings->ra_values = all_values;
+
+  // 4. all-to-all by A-position range, then 5. local sort of what arrived (G sorted pieces)
+  DeviceBuffer received, received_alt;
+  BWTM_TRY(received.allocate(std::max<uint64_t>(recv_total, 1) * sizeof(KeyT)));
+  BWTM_NCCL(api->GroupStart());
+  for(int peer = 0; peer < G; peer++)
+  {
+    if(send_count[peer] > 0) { BWTM_NCCL(api->Send(sorted + send_offset[peer], send_count[peer], NcclKey<KeyT>::type, peer, comm->comm, stream)); }
+    uint64_t incoming = recv_offset[peer + 1] - recv_offset[peer];
+    if(incoming > 0) { BWTM_NCCL(api->Recv(received.as<KeyT>() + recv_offset[peer], incoming, NcclKey<KeyT>::type, peer, comm->comm, stream)); }
+  }
+  BWTM_NCCL(api->GroupEnd());
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  keys.release(); alt.release();
+  KeyT* slice_keys = received.as<KeyT>();
+  if(recv_total > 0 && G > 1)
+  {
+    BWTM_TRY(received_alt.allocate(recv_total * sizeof(KeyT)));
+    BWTM_TRY(sort_keys<KeyT>(received.as<KeyT>(), received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream));
+  }
+  timings->exchange_seconds = timer.stop() * 1e-3;
+
+  // 6. my slice of the merged BWT
+  uint64_t a_lo = std::min<uint64_t>(splitter[r], n_a), a_hi = std::min<uint64_t>(splitter[r + 1], n_a);
+  uint64_t begin = a_lo + b_lo, end = a_hi + b_lo + recv_total;
+  uint64_t slab = clamp_slab(options->slab_symbols, end - begin);
+  bool single_slab = (end - begin <= slab);
+
+  DeviceBuffer merged, tile_j, control;
+  SlabEncoder encoder;
+  BWTM_TRY(control.allocate(sizeof(EncodeControl)));
+  float interleave_ms = 0.0f, encode_ms = 0.0f;
+  if(single_slab && end > begin)
+  {
+    BWTM_TRY(merged.allocate(slab));
+    BWTM_TRY(tile_j.allocate((slab / interleave_tile_size() + 2) * sizeof(uint64_t)));
+    BWTM_TRY(encoder.init(slab, stream));
+    timer.start();
+    BWTM_TRY(interleave_slab<KeyT>(a, b, slice_keys, b_lo, recv_total, begin, end, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream));
+    interleave_ms += timer.stop();
+    timer.start();
+    BWTM_TRY(encoder.detect(merged.as<uint8_t>(), end - begin, stream));
+    encode_ms += timer.stop();
+  }
+
+  // 7. the writer state comes from the previous slice and goes to the next one
+  if(r > 0)
+  {
+    BWTM_NCCL(api->Recv(control.ptr, sizeof(EncodeControl), ncclUint8, r - 1, comm->comm, stream));
+  }
+  else { BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream)); }
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  OutputBuffer out = { nullptr, 0, ctl.out_size };
+  uint64_t estimate = (a->rle_bytes + b->rle_bytes) / G;
+  int rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream);
+  timer.start();
+  if(rc == BWTM_OK && end > begin)
+  {
+    if(single_slab) { rc = encoder.write(&out, control.as<EncodeControl>(), stream); }
+    else
+    {
+      rc = interleave_range<KeyT>(a, b, slice_keys, b_lo, recv_total, begin, end, options->slab_symbols, &out,
+                                  control.as<EncodeControl>(), false, &interleave_ms, &encode_ms, stream);
+    }
+  }
+  if(rc == BWTM_OK && r == G - 1)
+  {
+    if(!single_slab || end == begin) { rc = encoder.init(4096, stream); }
+    if(rc == BWTM_OK) { rc = encoder.finish(&out, control.as<EncodeControl>(), stream); }
+  }
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  if(single_slab) { encode_ms += timer.stop(); } else { timer.stop(); }
+  if(r < G - 1) { BWTM_NCCL(api->Send(control.ptr, sizeof(EncodeControl), ncclUint8, r + 1, comm->comm, stream)); }
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  timings->interleave_seconds = interleave_ms * 1e-3;
+  timings->encode_seconds = encode_ms * 1e-3;
+  received.release(); received_alt.release(); merged.release();
+
+  // 8. every rank gets the complete run-length BWT
+  timer.start();
+  unsigned long long mine[3] = { out.origin, ctl.out_size - out.origin, ctl.runs_total };
+  std::vector<unsigned long long> slices((size_t)3 * G, 0);
+  DeviceBuffer d_mine, d_slices;
+  BWTM_TRY(d_mine.allocate(sizeof(mine))); BWTM_TRY(d_slices.allocate(slices.size() * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemcpyAsync(d_mine.ptr, mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
+  BWTM_NCCL(api->AllGather(d_mine.ptr, d_slices.ptr, 3, ncclUint64, comm->comm, stream));
+  BWTM_CUDA(cudaMemcpyAsync(slices.data(), d_slices.ptr, slices.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  uint64_t total_bytes = slices[(size_t)3 * (G - 1)] + slices[(size_t)3 * (G - 1) + 1];
+  timings->merged_bytes = total_bytes; timings->merged_runs = slices[(size_t)3 * (G - 1) + 2];
+  OutputBuffer full = { nullptr, 0, 0 };
+  rc = ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream);
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  for(int k = 0; k < G; k++)
+  {
+    uint64_t offset = slices[(size_t)3 * k], bytes = slices[(size_t)3 * k + 1];
+    if(bytes == 0) { continue; }
+    if(offset + bytes > total_bytes) { set_error("inconsistent slice layout"); device_free(out.ptr); device_free(full.ptr); return BWTM_ERR_INTERNAL; }
+    BWTM_NCCL(api->Broadcast(k == r ? (const void*)out.ptr : (const void*)(full.ptr + offset), full.ptr + offset, bytes, ncclUint8, k, comm->comm, stream));
+  }
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  device_free(out.ptr);
+  timings->exchange_seconds += timer.stop() * 1e-3;
+  (void)exchange_start;
+
+  // 9. replica of the rank structure
+  timer.start();
+  uint64_t counts[SIGMA];
+  for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
+  rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
+  device_free(full.ptr);
+  timings->index_seconds = timer.stop() * 1e-3;
+  return rc;
+}
+
+} // namespace bwtm
 
 extern "C"
 {
 
-int bwtm_comm_unique_id(uint8_t*) { set_error("multi-GPU merge is not built yet"); return BWTM_ERR_COMM; }
-int bwtm_comm_create(const uint8_t*, int, int, bwtm_comm**) { set_error("multi-GPU merge is not built yet"); return BWTM_ERR_COMM; }
-int bwtm_comm_destroy(bwtm_comm*) { return BWTM_OK; }
-int bwtm_merge_distributed(bwtm_comm*, bwtm_index*, bwtm_index*, const bwtm_merge_options*, bwtm_index**, bwtm_timings*)
+// Contiguous block of `total` items owned by `rank` of `world`: [first, first + count). The split of B's
+// sequence ids across GPUs (the reference's ParallelLoop blocks, utils.cpp:169-197, with one block per rank).
+int bwtm_shard_range(uint64_t total, uint32_t rank, uint32_t world, uint64_t* first, uint64_t* count)
 {
-  set_error("multi-GPU merge is not built yet"); return BWTM_ERR_COMM;
+  if(first == nullptr || count == nullptr || world == 0 || rank >= world) { set_error("invalid argument"); return BWTM_ERR_ARGUMENT; }
+  uint64_t begin = (uint64_t)(((__uint128_t)total * rank) / world);
+  uint64_t end = (uint64_t)(((__uint128_t)total * (rank + 1)) / world);
+  *first = begin; *count = end - begin;
+  return BWTM_OK;
+}
+
+int bwtm_comm_unique_id(uint8_t* id)
+{
+  if(id == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  NcclApi* api = nccl();
+  if(!api->ok) { set_error("libnccl.so.2 could not be loaded: %s", dlerror() ? dlerror() : "symbol missing"); return BWTM_ERR_COMM; }
+  static_assert(sizeof(ncclUniqueId) == BWTM_COMM_ID_BYTES, "ncclUniqueId size");
+  ncclUniqueId unique;
+  BWTM_NCCL(api->GetUniqueId(&unique));
+  std::memcpy(id, &unique, sizeof(unique));
+  return BWTM_OK;
+}
+
+int bwtm_comm_create(const uint8_t* id, int rank, int world, bwtm_comm** out)
+{
+  if(id == nullptr || out == nullptr || world < 1 || rank < 0 || rank >= world) { set_error("invalid argument"); return BWTM_ERR_ARGUMENT; }
+  *out = nullptr;
+  int count = 0;
+  if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+  {
+    cudaGetLastError(); set_error("no CUDA device available; this library has no CPU fallback"); return BWTM_ERR_CUDA;
+  }
+  NcclApi* api = nccl();
+  if(!api->ok) { set_error("libnccl.so.2 could not be loaded"); return BWTM_ERR_COMM; }
+  ncclUniqueId unique;
+  std::memcpy(&unique, id, sizeof(unique));
+  ncclComm_t comm;
+  BWTM_NCCL(api->CommInitRank(&comm, world, unique, rank));
+  bwtm_comm* c = new bwtm_comm();
+  c->comm = comm; c->rank = rank; c->world = world;
+  *out = c;
+  return BWTM_OK;
+}
+
+int bwtm_comm_destroy(bwtm_comm* comm)
+{
+  if(comm == nullptr) { return BWTM_OK; }
+  if(nccl()->ok) { nccl()->CommDestroy(comm->comm); }
+  delete comm;
+  return BWTM_OK;
+}
+
+int bwtm_merge_distributed(bwtm_comm* comm, bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options,
+                           bwtm_index** out, bwtm_timings* timings)
+{
+  bwtm_merge_options defaults; std::memset(&defaults, 0, sizeof(defaults));
+  if(options == nullptr) { options = &defaults; }
+  bwtm_timings local; std::memset(&local, 0, sizeof(local));
+  bool keep = (options->keep_inputs != 0);
+
+  int rc = BWTM_OK;
+  if(comm == nullptr || a == nullptr || b == nullptr || out == nullptr) { set_error("null argument"); rc = BWTM_ERR_ARGUMENT; }
+  else if(a->d_records == nullptr || b->d_records == nullptr) { set_error("an input has no rank structure (it was built with skip_index)"); rc = BWTM_ERR_ARGUMENT; }
+  else if(b->sequences == 0) { set_error("the inserted BWT has no sequences"); rc = BWTM_ERR_ARGUMENT; }
+  if(rc == BWTM_OK)
+  {
+    *out = nullptr;
+    uint64_t launches_before = bwtm_kernel_launches();
+    auto start = std::chrono::steady_clock::now();
+    if(a->size < 0xFFFFFFFFull) { rc = merge_distributed_impl<uint32_t>(comm, a, b, options, out, &local); }
+    else { rc = merge_distributed_impl<uint64_t>(comm, a, b, options, out, &local); }
+    cudaDeviceSynchronize();
+    local.total_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    local.kernel_launches = bwtm_kernel_launches() - launches_before;
+  }
+  if(!keep) { index_free(a); index_free(b); }
+  if(timings != nullptr) { *timings = local; }
+  return rc;
 }
 
 } // extern "C"

@@ -306,9 +306,12 @@ __global__ void enc_write(const EncodeControl* ctl, const uint8_t* __restrict__ 
 //------------------------------------------------------------------------------
 // Host orchestration
 
+// `needed` and `valid_bytes` are global offsets (see OutputBuffer::origin).
 int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cudaStream_t stream)
 {
-  if(needed <= out->capacity) { return BWTM_OK; }
+  needed = (needed > out->origin ? needed - out->origin : 0);
+  valid_bytes = (valid_bytes > out->origin ? valid_bytes - out->origin : 0);
+  if(needed <= out->capacity && out->ptr != nullptr) { return BWTM_OK; }
   uint64_t capacity = std::max(needed + (needed >> 2), (uint64_t)(1 << 20));
   DeviceBuffer bigger; BWTM_TRY(bigger.allocate(capacity));
   if(out->ptr != nullptr && valid_bytes > 0)
@@ -321,25 +324,6 @@ int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cu
   out->capacity = capacity;
   return BWTM_OK;
 }
-
-struct EventTimer
-{
-  cudaEvent_t begin, end;
-  cudaStream_t stream;
-  bool ok;
-  explicit EventTimer(cudaStream_t s) : stream(s)
-  {
-    ok = (cudaEventCreate(&begin) == cudaSuccess && cudaEventCreate(&end) == cudaSuccess);
-  }
-  ~EventTimer() { if(ok) { cudaEventDestroy(begin); cudaEventDestroy(end); } }
-  void start() { if(ok) { cudaEventRecord(begin, stream); } }
-  float stop()
-  {
-    if(!ok) { return 0.0f; }
-    cudaEventRecord(end, stream); cudaEventSynchronize(end);
-    float ms = 0.0f; cudaEventElapsedTime(&ms, begin, end); return ms;
-  }
-};
 
 int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
 {
@@ -366,28 +350,36 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   return BWTM_OK;
 }
 
-// K3 + K5 for `symbols` consecutive symbols of the sequence being written.
-int SlabEncoder::encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+// K3: maximal runs of `symbols` consecutive symbols.
+int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream)
 {
+  detected_runs = 0;
   if(symbols == 0) { return BWTM_OK; }
   if(symbols > max_symbols) { set_error("slab of %llu symbols exceeds the encoder capacity", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
   size_t temp_bytes = cub_temp.bytes;
-  EncodeControl ctl;
-
-  // K3: maximal runs of the slab
   BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, sizeof(uint64_t), stream));
   BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(cub_temp.ptr, temp_bytes, d_symbols, run_sym.as<uint8_t>(),
                                                 run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)symbols, stream));
   count_launch(3);
   uint64_t m = 0;
   BWTM_CUDA(cudaMemcpyAsync(&m, num_runs.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   if(m == 0) { set_error("run-length encode produced no runs for %llu symbols", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
+  detected_runs = m;
+  return BWTM_OK;
+}
 
-  // K5
+// K5: byte-exact Run::write of the detected runs, continuing from the state in d_control.
+int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+{
+  uint64_t m = detected_runs;
+  if(m == 0) { return BWTM_OK; }
+  size_t temp_bytes = cub_temp.bytes;
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
   BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.out_size, stream));
-  enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_len.as<uint32_t>(), m, out->ptr, 0);
+  enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_len.as<uint32_t>(), m, out->at_origin(), 0);
   BWTM_LAUNCH_CHECK();
   BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
@@ -421,9 +413,15 @@ int SlabEncoder::encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer
   BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.slab_base, stream));
-  enc_write<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(d_control, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), count, out->ptr);
+  enc_write<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(d_control, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), count, out->at_origin());
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
+}
+
+int SlabEncoder::encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+{
+  BWTM_TRY(this->detect(d_symbols, symbols, stream));
+  return this->write(out, d_control, stream);
 }
 
 // Flushes the pending run (bwt.cpp:279-281).
@@ -433,7 +431,7 @@ int SlabEncoder::finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_
   BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.out_size, stream));
-  enc_head<<<1, 1, 0, stream>>>(d_control, nullptr, nullptr, 0, out->ptr, 1);
+  enc_head<<<1, 1, 0, stream>>>(d_control, nullptr, nullptr, 0, out->at_origin(), 1);
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }
@@ -446,6 +444,24 @@ uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total)
   return std::min(slab_symbols, div_up(std::max(total, (uint64_t)1), TILE) * TILE);
 }
 
+uint64_t interleave_tile_size() { return TILE; }
+
+template<class KeyT>
+int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
+                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream)
+{
+  if(p1 <= p0) { return BWTM_OK; }
+  uint64_t tiles = div_up(p1 - p0, TILE);
+  k4_partition<KeyT><<<(unsigned)div_up(tiles + 1, 256), 256, 0, stream>>>(d_keys, key_base, key_count, p0, p1, tiles, d_tile_j);
+  BWTM_LAUNCH_CHECK();
+  k4_interleave<KeyT><<<(unsigned)tiles, IL_THREADS, 0, stream>>>(device_view(a), device_view(b), d_keys, key_base, d_tile_j, p0, p1, d_merged);
+  BWTM_LAUNCH_CHECK();
+  return BWTM_OK;
+}
+
+template int interleave_slab<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t);
+template int interleave_slab<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t);
+
 template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
                      uint64_t begin, uint64_t end, uint64_t slab_symbols,
@@ -456,28 +472,20 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
   uint64_t max_tiles = slab_symbols / TILE;
   DeviceBuffer merged, tile_j;
   BWTM_TRY(merged.allocate(slab_symbols));
-  BWTM_TRY(tile_j.allocate((max_tiles + 1) * sizeof(uint64_t)));
+  BWTM_TRY(tile_j.allocate((max_tiles + 2) * sizeof(uint64_t)));
   SlabEncoder encoder;
   BWTM_TRY(encoder.init(slab_symbols, stream));
-
-  DeviceIndex va = device_view(a), vb = device_view(b);
   EventTimer timer(stream);
 
   for(uint64_t p0 = begin; p0 < end; p0 += slab_symbols)
   {
     uint64_t p1 = std::min(p0 + slab_symbols, end);
-    uint64_t symbols = p1 - p0;
-    uint64_t tiles = div_up(symbols, TILE);
-
     timer.start();
-    k4_partition<KeyT><<<(unsigned)div_up(tiles + 1, 256), 256, 0, stream>>>(d_keys, key_base, key_count, p0, p1, tiles, tile_j.as<uint64_t>());
-    BWTM_LAUNCH_CHECK();
-    k4_interleave<KeyT><<<(unsigned)tiles, IL_THREADS, 0, stream>>>(va, vb, d_keys, key_base, tile_j.as<uint64_t>(), p0, p1, merged.as<uint8_t>());
-    BWTM_LAUNCH_CHECK();
+    BWTM_TRY(interleave_slab<KeyT>(a, b, d_keys, key_base, key_count, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream));
     *interleave_ms += timer.stop();
 
     timer.start();
-    BWTM_TRY(encoder.encode(merged.as<uint8_t>(), symbols, out, d_control, stream));
+    BWTM_TRY(encoder.encode(merged.as<uint8_t>(), p1 - p0, out, d_control, stream));
     *encode_ms += timer.stop();
   }
 
@@ -497,7 +505,7 @@ template int interleave_range<uint64_t>(const bwtm_index*, const bwtm_index*, co
 
 //------------------------------------------------------------------------------
 
-static int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } return (n == 0 ? 1 : n); }
+int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } return (n == 0 ? 1 : n); }
 
 template<class KeyT>
 __global__ void count_distinct(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ result)
@@ -510,7 +518,7 @@ __global__ void count_distinct(const KeyT* __restrict__ keys, uint64_t n, unsign
 
 // Wraps freshly encoded RLE bytes into an index (K0 unless skipped). `counts` (6 values) are the
 // expected per-comp counts, or NULL.
-static int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
+int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
                         cudaStream_t stream, bwtm_index** result)
 {
   DeviceBuffer exact; BWTM_TRY(exact.allocate(rle_bytes + RLE_PADDING));
@@ -557,7 +565,7 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   SlabEncoder encoder; BWTM_TRY(encoder.init(slab, stream));
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
-  OutputBuffer buffer = { nullptr, 0 };
+  OutputBuffer buffer = { nullptr, 0, 0 };
   int rc = ensure_capacity(&buffer, n / 4 + (1 << 20), 0, stream);
   for(uint64_t p0 = 0; rc == BWTM_OK && p0 < n; p0 += slab)
   {
@@ -617,7 +625,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
 
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
-  OutputBuffer out = { nullptr, 0 };
+  OutputBuffer out = { nullptr, 0, 0 };
   int rc = ensure_capacity(&out, a->rle_bytes + b->rle_bytes + ((a->rle_bytes + b->rle_bytes) >> 2) + (1 << 20), 0, stream);
   float interleave_ms = 0.0f, encode_ms = 0.0f;
   if(rc == BWTM_OK)

@@ -38,6 +38,28 @@ struct OutputBuffer
 {
   uint8_t* ptr;
   uint64_t capacity;
+  uint64_t origin;     // global byte offset of ptr[0]: a GPU slice of the output starts where the previous slice ended
+  uint8_t* at_origin() const { return ptr - origin; }   // kernels index this with global offsets
+};
+
+// CUDA-event stopwatch on one stream.
+struct EventTimer
+{
+  cudaEvent_t begin, end;
+  cudaStream_t stream;
+  bool ok;
+  explicit EventTimer(cudaStream_t s) : stream(s)
+  {
+    ok = (cudaEventCreate(&begin) == cudaSuccess && cudaEventCreate(&end) == cudaSuccess);
+  }
+  ~EventTimer() { if(ok) { cudaEventDestroy(begin); cudaEventDestroy(end); } }
+  void start() { if(ok) { cudaEventRecord(begin, stream); } }
+  float stop()
+  {
+    if(!ok) { return 0.0f; }
+    cudaEventRecord(end, stream); cudaEventSynchronize(end);
+    float ms = 0.0f; cudaEventElapsedTime(&ms, begin, end); return ms;
+  }
 };
 
 // K3 + K5 on a stream of symbol slabs: run detection and the byte-exact Run::write.
@@ -45,7 +67,12 @@ struct SlabEncoder
 {
   uint64_t max_symbols;
   DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, cub_temp;
+  uint64_t detected_runs;   // result of detect()
   int init(uint64_t max_symbols, cudaStream_t stream);
+  // K3: maximal runs of the slab; independent of the encoder state.
+  int detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream);
+  // K5: writes the runs found by detect() continuing from the state in d_control.
+  int write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
   int encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
   int finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
 };
@@ -56,8 +83,19 @@ int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cu
 // Symbols of a complete sequence (device, one comp per byte) -> index. Used by the fixture builder.
 int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out);
 
+// Wraps encoded RLE bytes (out->ptr[0 .. rle_bytes)) into an index; frees the buffer. counts may be NULL unless skip_index.
+int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
+                 cudaStream_t stream, bwtm_index** result);
+int bit_length_host(uint64_t v);
+
 int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
                 bwtm_index** result, bwtm_timings* timings);
+
+// K4 for one slab: merged symbols of positions [p0, p1) into `merged` (tile_j: (p1 - p0) / 4096 + 2 entries).
+template<class KeyT>
+int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
+                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream);
+uint64_t interleave_tile_size();
 
 template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,

@@ -171,6 +171,10 @@ int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first
    sequences of b are split across ranks, RA values are exchanged by A-position range with one NCCL
    all-to-all and every rank interleaves a contiguous slice of the merged BWT. */
 
+/* Contiguous block [first, first + count) of `total` items owned by `rank` of `world`: the split of B's
+   sequence ids across GPUs (one ParallelLoop block per rank, utils.cpp:169-197). Pure host arithmetic. */
+int bwtm_shard_range(uint64_t total, uint32_t rank, uint32_t world, uint64_t* first, uint64_t* count);
+
 #define BWTM_COMM_ID_BYTES 128
 int bwtm_comm_unique_id(uint8_t id[BWTM_COMM_ID_BYTES]);               /* rank 0; broadcast it by any means */
 int bwtm_comm_create(const uint8_t id[BWTM_COMM_ID_BYTES], int rank, int world, bwtm_comm** out);

@@ -1,0 +1,45 @@
+"""Launched by torchrun on N GPUs (tests/test_gpu_dist.py): distributed merge == single-GPU merge == oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "bwt-merge_b200"))
+
+import bwtm_b200                                    # noqa: E402
+from bwtm_b200 import FMI, MergeParameters, synth   # noqa: E402
+
+
+def main():
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); local = int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local); bwtm_b200.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
+    thr = synth.error_threshold(0.01)
+    cases = [(200000, 20000, 100, 0), (50000, 3000, 60, 8192), (3000, 5, 40, 4096), (100, 1, 30, 0)]
+    for G, n, L, slab in cases:
+        A = FMI.synthetic(G, 42, L, thr, [(1, n)]); B = FMI.synthetic(G, 42, L, thr, [(2, max(1, n // 2))])
+        p = MergeParameters(); p.slab_symbols = slab
+        single = FMI.merge(A, B, p, keep_inputs=True)
+        multi = comm.merge(A, B, p, keep_inputs=True)
+        want = single.rle()
+        got = multi.rle()
+        assert np.array_equal(got, want), "rank %d: distributed merge differs (case %s)" % (rank, (G, n, L, slab))
+        assert np.array_equal(multi.counts(), single.counts()) and multi.hash() == single.hash()
+        # sequential: the distributed result is the next A on every rank
+        C_ = FMI.synthetic(G, 42, L, thr, [(3, max(1, n // 3))])
+        again = comm.merge(multi, C_, p, keep_inputs=True)
+        direct = FMI.synthetic(G, 42, L, thr, [(1, n), (2, max(1, n // 2)), (3, max(1, n // 3))])
+        assert np.array_equal(again.rle(), direct.rle()), "rank %d: sequential distributed merge differs" % rank
+    dist.barrier()
+    if rank == 0:
+        print("dist_check ok: %d ranks, %d cases" % (world, len(cases)))
+    comm.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
