@@ -273,6 +273,9 @@ def main():
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     stage = {k: 0.0 for k in ("search", "sort", "exchange", "interleave", "encode", "index")}
     last = None
+    profiling = os.environ.get("BWTM_PROFILE_RANGE") == "1"   # ncu --profile-from-start off
+    if profiling:
+        torch.cuda.profiler.start()
     start.record()
     for _ in range(args.steps):
         M = one_merge()
@@ -283,6 +286,8 @@ def main():
         M.close()
     end.record()
     barrier()
+    if profiling:
+        torch.cuda.profiler.stop()
     clocks = sampler.stop()
     launches = bwtm_b200.kernel_launches() - launches0
     ms_total = start.elapsed_time(end)

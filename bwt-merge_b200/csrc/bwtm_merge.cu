@@ -28,6 +28,8 @@ constexpr int TILE        = 4096;
 constexpr int IL_THREADS  = 256;
 constexpr int PER_THREAD  = TILE / IL_THREADS;   // 16
 constexpr int LONG_TILE   = 1024;                // long runs per transducer tile
+constexpr int LONG_SUB    = 32;                  // long runs per checkpointed sub-tile
+constexpr int SCAN_CHUNK  = 128;                 // tile maps staged in shared memory per step of the tile scan
 
 //------------------------------------------------------------------------------
 // K4
@@ -235,56 +237,108 @@ __global__ void enc_collect_long(EncodeControl* ctl, const uint32_t* __restrict_
   }
 }
 
-// Transducer tile maps: bytes produced by the tile's long runs for each of the 64 residues of
-// "bytes produced by earlier long runs".
+// Bytes of a long run at output offset `state` (mod 64), given its natural size (head + full extension):
+// the natural encoding is used whenever it fits into the rest of the block (support.h:267-280).
+__device__ __forceinline__ uint32_t long_run_bytes_fast(uint32_t length, uint32_t natural, uint32_t state)
+{
+  return (RLE_BLOCK - state >= natural ? natural : long_run_bytes(length, state));
+}
+
+__device__ __forceinline__ uint32_t natural_bytes(uint32_t length)   // length >= MAX_RUN
+{
+  return 1u + bytecode_length((uint64_t)length - MAX_RUN);
+}
+
+// Transducer tile maps: bytes produced by the tile's long runs for each of the 64 residues of "bytes
+// produced by earlier long runs", with a checkpoint every LONG_SUB runs.
 __global__ void __launch_bounds__(64)
 enc_tile_maps(const EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
-              const uint32_t* __restrict__ long_list, uint64_t n_long, uint32_t* __restrict__ tile_bytes)
+              const uint32_t* __restrict__ long_list, uint64_t n_long, uint32_t* __restrict__ tile_bytes,
+              uint16_t* __restrict__ checkpoints)
 {
+  __shared__ uint32_t s_len[LONG_SUB], s_nat[LONG_SUB], s_before[LONG_SUB];
   uint32_t base_state = (uint32_t)(ctl->slab_base & 63u);
   uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
   uint64_t last = (first + LONG_TILE < n_long ? first + LONG_TILE : n_long);
   uint32_t p = threadIdx.x;
-  for(uint64_t k = first; k < last; k++)
+  for(uint64_t chunk = first; chunk < last; chunk += LONG_SUB)
   {
-    uint32_t idx = long_list[k];
-    uint32_t state = (base_state + (uint32_t)scan[idx] + p) & 63u;
-    p += long_run_bytes(len[idx], state);
+    uint64_t sub = chunk / LONG_SUB;
+    checkpoints[sub * 64 + threadIdx.x] = (uint16_t)(p - threadIdx.x);
+    __syncthreads();
+    if(threadIdx.x < LONG_SUB && chunk + threadIdx.x < last)
+    {
+      uint32_t idx = long_list[chunk + threadIdx.x];
+      uint32_t length = len[idx];
+      s_len[threadIdx.x] = length; s_nat[threadIdx.x] = natural_bytes(length);
+      s_before[threadIdx.x] = base_state + (uint32_t)scan[idx];
+    }
+    __syncthreads();
+    int count = (int)(last - chunk < (uint64_t)LONG_SUB ? last - chunk : (uint64_t)LONG_SUB);
+    for(int k = 0; k < count; k++)
+    {
+      uint32_t state = (s_before[k] + p) & 63u;
+      p += long_run_bytes_fast(s_len[k], s_nat[k], state);
+    }
   }
   tile_bytes[(uint64_t)blockIdx.x * 64 + threadIdx.x] = p - threadIdx.x;
 }
 
-__global__ void enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint64_t tiles,
-                              unsigned long long* __restrict__ tile_entry)
+// Composition of the tile maps in order; the maps are staged through shared memory so that every
+// dependent step is a shared-memory lookup.
+__global__ void __launch_bounds__(256)
+enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint64_t tiles,
+              unsigned long long* __restrict__ tile_entry)
 {
-  if(blockIdx.x != 0 || threadIdx.x != 0) { return; }
-  unsigned long long p = 0;
-  for(uint64_t t = 0; t < tiles; t++)
+  __shared__ uint32_t staged[SCAN_CHUNK * 64];
+  __shared__ unsigned long long entries[SCAN_CHUNK];
+  __shared__ unsigned long long carried;
+  if(threadIdx.x == 0) { carried = 0; }
+  __syncthreads();
+  for(uint64_t first = 0; first < tiles; first += SCAN_CHUNK)
   {
-    tile_entry[t] = p;
-    p += tile_bytes[t * 64 + (p & 63u)];
+    uint64_t count = (tiles - first < (uint64_t)SCAN_CHUNK ? tiles - first : (uint64_t)SCAN_CHUNK);
+    for(uint64_t k = threadIdx.x; k < count * 64; k += blockDim.x) { staged[k] = tile_bytes[first * 64 + k]; }
+    __syncthreads();
+    if(threadIdx.x == 0)
+    {
+      unsigned long long p = carried;
+      for(uint64_t t = 0; t < count; t++) { entries[t] = p; p += staged[t * 64 + (p & 63u)]; }
+      carried = p;
+    }
+    __syncthreads();
+    for(uint64_t t = threadIdx.x; t < count; t += blockDim.x) { tile_entry[first + t] = entries[t]; }
+    __syncthreads();
   }
-  ctl->long_bytes = p;
-  ctl->out_size = ctl->slab_base + ctl->n_short + p;
-  ctl->runs_total += ctl->count;
+  if(threadIdx.x == 0)
+  {
+    ctl->long_bytes = carried;
+    ctl->out_size = ctl->slab_base + ctl->n_short + carried;
+    ctl->runs_total += ctl->count;
+  }
 }
 
+// One thread per sub-tile of LONG_SUB long runs: starts from the tile's true entry and the checkpoint of
+// that entry residue.
 __global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
-                                 const uint32_t* __restrict__ long_list, uint64_t n_long, uint64_t tiles,
-                                 const unsigned long long* __restrict__ tile_entry, uint32_t* __restrict__ long_offset)
+                                 const uint32_t* __restrict__ long_list, uint64_t n_long,
+                                 const unsigned long long* __restrict__ tile_entry, const uint16_t* __restrict__ checkpoints,
+                                 uint32_t* __restrict__ long_offset)
 {
-  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(t >= tiles) { return; }
+  uint64_t sub = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  uint64_t first = sub * LONG_SUB;
+  if(first >= n_long) { return; }
+  uint64_t last = (first + LONG_SUB < n_long ? first + LONG_SUB : n_long);
   uint32_t base_state = (uint32_t)(ctl->slab_base & 63u);
-  uint64_t first = t * LONG_TILE;
-  uint64_t last = (first + LONG_TILE < n_long ? first + LONG_TILE : n_long);
-  unsigned long long p = tile_entry[t];
+  unsigned long long entry = tile_entry[first / LONG_TILE];
+  unsigned long long p = entry + checkpoints[sub * 64 + (entry & 63u)];
   for(uint64_t k = first; k < last; k++)
   {
     uint32_t idx = long_list[k];
+    uint32_t length = len[idx];
     long_offset[k] = (uint32_t)p;
     uint32_t state = (base_state + (uint32_t)scan[idx] + (uint32_t)p) & 63u;
-    p += long_run_bytes(len[idx], state);
+    p += long_run_bytes_fast(length, natural_bytes(length), state);
   }
 }
 
@@ -338,6 +392,7 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
   BWTM_TRY(tile_bytes.allocate(max_long_tiles * 64 * sizeof(uint32_t)));
   BWTM_TRY(tile_entry.allocate(max_long_tiles * sizeof(unsigned long long)));
+  BWTM_TRY(checkpoints.allocate((max_long / LONG_SUB + 1) * 64 * sizeof(uint16_t)));
 
   size_t rle_temp = 0, scan_temp = 0;
   BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_temp, (const uint8_t*)nullptr, run_sym.as<uint8_t>(),
@@ -399,15 +454,17 @@ int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t
   uint64_t long_tiles = div_up(n_long, LONG_TILE);
   if(long_tiles > 0)
   {
-    enc_tile_maps<<<(unsigned)long_tiles, 64, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), n_long, tile_bytes.as<uint32_t>());
+    enc_tile_maps<<<(unsigned)long_tiles, 64, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), n_long,
+                                                           tile_bytes.as<uint32_t>(), checkpoints.as<uint16_t>());
     BWTM_LAUNCH_CHECK();
   }
-  enc_tile_scan<<<1, 1, 0, stream>>>(d_control, tile_bytes.as<uint32_t>(), long_tiles, tile_entry.as<unsigned long long>());
+  enc_tile_scan<<<1, 256, 0, stream>>>(d_control, tile_bytes.as<uint32_t>(), long_tiles, tile_entry.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
   if(long_tiles > 0)
   {
-    enc_long_offsets<<<(unsigned)div_up(long_tiles, 128), 128, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(),
-                                                                           n_long, long_tiles, tile_entry.as<unsigned long long>(), long_offset.as<uint32_t>());
+    enc_long_offsets<<<(unsigned)div_up(div_up(n_long, LONG_SUB), 128), 128, 0, stream>>>(
+      d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), n_long,
+      tile_entry.as<unsigned long long>(), checkpoints.as<uint16_t>(), long_offset.as<uint32_t>());
     BWTM_LAUNCH_CHECK();
   }
   BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
@@ -507,13 +564,24 @@ template int interleave_range<uint64_t>(const bwtm_index*, const bwtm_index*, co
 
 int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } return (n == 0 ? 1 : n); }
 
+// Number of distinct values of a sorted array: the reference's RA run count (support.h:421-428).
 template<class KeyT>
-__global__ void count_distinct(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ result)
+__global__ void __launch_bounds__(256)
+count_distinct(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ result)
 {
-  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  bool boundary = (k < n) && (k == 0 || keys[k] != keys[k - 1]);
-  unsigned mask = __ballot_sync(0xFFFFFFFFu, boundary);
-  if((threadIdx.x & 31) == 0 && mask != 0) { atomicAdd(result, (unsigned long long)__popc(mask)); }
+  __shared__ unsigned int block_total;
+  if(threadIdx.x == 0) { block_total = 0; }
+  __syncthreads();
+  unsigned int local = 0;
+  for(uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x)
+  {
+    local += (k == 0 || keys[k] != keys[k - 1]) ? 1u : 0u;
+  }
+#pragma unroll
+  for(int offset = 16; offset > 0; offset >>= 1) { local += __shfl_down_sync(0xFFFFFFFFu, local, offset); }
+  if((threadIdx.x & 31) == 0 && local != 0) { atomicAdd(&block_total, local); }
+  __syncthreads();
+  if(threadIdx.x == 0 && block_total != 0) { atomicAdd(result, (unsigned long long)block_total); }
 }
 
 // Wraps freshly encoded RLE bytes into an index (K0 unless skipped). `counts` (6 values) are the
@@ -615,7 +683,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   {
     DeviceBuffer distinct; BWTM_TRY(distinct.allocate(sizeof(unsigned long long)));
     BWTM_CUDA(cudaMemsetAsync(distinct.ptr, 0, sizeof(unsigned long long), stream));
-    count_distinct<KeyT><<<(unsigned)div_up(n_b, 256), 256, 0, stream>>>(sorted, n_b, distinct.as<unsigned long long>());
+    count_distinct<KeyT><<<(unsigned)std::min<uint64_t>(div_up(n_b, 256), 148 * 16), 256, 0, stream>>>(sorted, n_b, distinct.as<unsigned long long>());
     BWTM_LAUNCH_CHECK();
     unsigned long long runs = 0;
     BWTM_CUDA(cudaMemcpyAsync(&runs, distinct.ptr, sizeof(runs), cudaMemcpyDeviceToHost, stream));

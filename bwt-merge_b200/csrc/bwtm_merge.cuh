@@ -66,7 +66,7 @@ struct EventTimer
 struct SlabEncoder
 {
   uint64_t max_symbols;
-  DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, cub_temp;
+  DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, cub_temp;
   uint64_t detected_runs;   // result of detect()
   int init(uint64_t max_symbols, cudaStream_t stream);
   // K3: maximal runs of the slab; independent of the encoder state.
