@@ -153,36 +153,34 @@ __device__ __forceinline__ uint4 load_chunk_64B(const uint4* p)
   return r;
 }
 
-// One LF / rank step of a 4-lane group on `idx` at position `pos` for comp `comp` (1..5):
-// returns C-less rank = (count before the record) + (count inside the record before pos).
-__device__ __forceinline__ uint64_t coop_rank(const DeviceIndex& idx, const uint4& q, uint64_t pos, uint32_t comp,
-                                              unsigned mask, int sub, int group_base)
+// In-record part of a cooperative rank: (count of comp before `pos` inside the record) + (the record's
+// header counter of comp). `q` is this lane's chunk; the caller adds the superblock and C counters.
+__device__ __forceinline__ uint32_t coop_record_rank(const uint4& q, uint32_t offset, uint32_t comp,
+                                                     unsigned mask, int sub, int group_base)
 {
-  uint32_t offset = (uint32_t)(pos & (RECORD_SYMBOLS - 1));
   int k = (int)offset - 32 * sub;
   k = (k < 0 ? 0 : k);
   uint32_t count = __popc(match_mask(q, comp) & low_mask(k));
   count += __shfl_xor_sync(mask, count, 1);
   count += __shfl_xor_sync(mask, count, 2);
-  uint32_t s = 25u * ((comp - 1u) & 7u);
+  uint32_t s = 25u * (comp - 1u);
   uint32_t w = s >> 5, shift = s & 31u;
   uint32_t lo = __shfl_sync(mask, q.w, group_base + (int)w);
   uint32_t hi = __shfl_sync(mask, q.w, group_base + (int)(w < 3 ? w + 1 : 3));
-  uint32_t field = __funnelshift_r(lo, hi, shift) & FIELD_MASK;
-  uint64_t record = pos >> RECORD_SHIFT;
-  return __ldg(idx.super + (record >> SUPER_RECORD_SHIFT) * SUPER_STRIDE + comp) + field + count;
+  return (__funnelshift_r(lo, hi, shift) & FIELD_MASK) + count;
 }
 
-template<class KeyT>
+// PosT = uint32_t when both BWTs are shorter than 2^32 (halves the address and rank arithmetic).
+template<class KeyT, class PosT>
 __global__ void __launch_bounds__(WALK_THREADS, 8)
 k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
              KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters)
 {
   __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
-  __shared__ uint64_t c_a[8], c_b[8];
+  __shared__ PosT c_a[8], c_b[8];
 
 #pragma unroll
-  for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = a.C[c]; c_b[c] = b.C[c]; } }
+  for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = (PosT)a.C[c]; c_b[c] = (PosT)b.C[c]; } }
   __syncthreads();
 
   const unsigned FULL = 0xFFFFFFFFu;
@@ -192,12 +190,14 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
   const int group_base = lane & ~(COOP_LANES - 1);
   const unsigned leaders_below = LEADERS & ((1u << group_base) - 1u);
   KeyT* stage = stage_all[threadIdx.x >> 5];
-  const uint64_t first_rank = a.sequences;
+  const PosT first_rank = (PosT)a.sequences;
+  const uint4* __restrict__ records_a = a.records + sub;
+  const uint4* __restrict__ records_b = b.records + sub;
 
   uint32_t fill = 0;          // warp-uniform
   bool exhausted = false;     // warp-uniform
   bool alive = false;         // uniform within a group
-  uint64_t pos_a = 0, pos_b = 0;
+  PosT pos_a = 0, pos_b = 0;
 
   while(true)
   {
@@ -212,7 +212,7 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
       if(!alive)
       {
         uint64_t mine = first + __popc(need & leaders_below);
-        if(mine < seq_end) { alive = true; pos_b = mine; pos_a = first_rank; }
+        if(mine < seq_end) { alive = true; pos_b = (PosT)mine; pos_a = first_rank; }
       }
       if(first + wanted >= seq_end) { exhausted = true; }
     }
@@ -220,6 +220,15 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
     unsigned active = __ballot_sync(FULL, alive);
     if(active == 0) { break; }
 
+    // Both record reads of this step are issued first: neither address depends on the other's data.
+    uint4 qb = make_uint4(0, 0, 0, 0), qa = make_uint4(0, 0, 0, 0);
+    if(alive)
+    {
+      qb = load_chunk_64B(records_b + 4 * (size_t)(pos_b >> RECORD_SHIFT));
+      qa = load_chunk_64B(records_a + 4 * (size_t)(pos_a >> RECORD_SHIFT));
+    }
+
+    // Emit the rank of the current suffix (fmi.cpp:290 with a run of length 1) while the loads fly.
     if(alive && sub == 0) { stage[fill + __popc(active & leaders_below)] = (KeyT)pos_a; }
     fill += __popc(active & LEADERS);
     if(fill > WALK_STAGE - 8)
@@ -245,17 +254,16 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
 
     if(alive)
     {
-      // (c, b') = LF_B(b): FMI::LF(i), fmi.h:147-150
-      uint4 qb = load_chunk_64B(b.records + 4 * (pos_b >> RECORD_SHIFT) + sub);
-      uint32_t offset = (uint32_t)(pos_b & (RECORD_SYMBOLS - 1));
-      uint32_t t = offset & 31u;
+      // (c, b') = LF_B(b): FMI::LF(i), fmi.h:147-150;  a' = LF_A(a, c): FMI::LF(i, c), fmi.h:152-155
+      uint32_t offset_b = (uint32_t)pos_b & (RECORD_SYMBOLS - 1), offset_a = (uint32_t)pos_a & (RECORD_SYMBOLS - 1);
+      uint32_t t = offset_b & 31u;
       uint32_t mine = ((qb.x >> t) & 1u) | (((qb.y >> t) & 1u) << 1) | (((qb.z >> t) & 1u) << 2);
-      uint32_t comp = __shfl_sync(active, mine, group_base + (int)(offset >> 5));
-      // a' = LF_A(a, c): FMI::LF(i, c), fmi.h:152-155. Issued before B's rank arithmetic: both records in flight.
-      uint4 qa = load_chunk_64B(a.records + 4 * (pos_a >> RECORD_SHIFT) + sub);
+      uint32_t comp = __shfl_sync(active, mine, group_base + (int)(offset_b >> 5));
       uint32_t safe = (comp == 0 ? 1u : comp);
-      uint64_t next_b = c_b[safe] + coop_rank(b, qb, pos_b, safe, active, sub, group_base);
-      uint64_t next_a = c_a[safe] + coop_rank(a, qa, pos_a, safe, active, sub, group_base);
+      PosT super_b = (PosT)__ldg(b.super + (size_t)(pos_b >> SUPER_SHIFT) * SUPER_STRIDE + safe);
+      PosT super_a = (PosT)__ldg(a.super + (size_t)(pos_a >> SUPER_SHIFT) * SUPER_STRIDE + safe);
+      PosT next_b = c_b[safe] + super_b + coop_record_rank(qb, offset_b, safe, active, sub, group_base);
+      PosT next_a = c_a[safe] + super_a + coop_record_rank(qa, offset_a, safe, active, sub, group_base);
       if(comp == 0) { alive = false; }
       else { pos_b = next_b; pos_a = next_a; }
     }
@@ -273,6 +281,20 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
     }
     else if(lane == 0) { counters->overflow = 1; }
   }
+}
+
+template<class KeyT, class PosT>
+static int launch_coop(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                       KeyT* d_out, uint64_t capacity, WalkCounters* counters, int sms, cudaStream_t stream)
+{
+  int per_sm = 0;
+  BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_coop<KeyT, PosT>, WALK_THREADS, 0));
+  if(per_sm < 1) { per_sm = 1; }
+  uint64_t sequences = seq_last + 1 - seq_first;
+  uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS / COOP_LANES));
+  k1_walk_coop<KeyT, PosT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
+    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters);
+  return BWTM_OK;
 }
 
 template<class KeyT>
@@ -295,13 +317,13 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
     k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
       device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
   }
+  else if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull)
+  {
+    BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, counters.as<WalkCounters>(), sms, stream)));
+  }
   else
   {
-    BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_coop<KeyT>, WALK_THREADS, 0));
-    if(per_sm < 1) { per_sm = 1; }
-    uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS / COOP_LANES));
-    k1_walk_coop<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
-      device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
+    BWTM_TRY((launch_coop<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, counters.as<WalkCounters>(), sms, stream)));
   }
   BWTM_LAUNCH_CHECK();
 
