@@ -17,11 +17,15 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <chrono>
 #include <vector>
 
 #include <nccl.h>
+
+#include <cub/cub.cuh>
 
 #include "bwtm_merge.cuh"
 
@@ -113,9 +117,57 @@ __global__ void lower_bounds(const KeyT* __restrict__ keys, uint64_t n, const un
   out[k] = lo;
 }
 
+// Merges the sorted pieces [offsets[k], offsets[k+1]) of `src` pairwise, ping-ponging between two buffers
+// (log2 G streaming rounds instead of another radix sort). *result points to the buffer with the answer.
+template<class KeyT>
+static int merge_sorted_pieces(KeyT* src, KeyT* dst, std::vector<uint64_t> offsets, cudaStream_t stream, KeyT** result)
+{
+  DeviceBuffer temp;
+  while(offsets.size() > 2)
+  {
+    std::vector<uint64_t> next; next.push_back(0);
+    for(size_t k = 0; k + 1 < offsets.size(); k += 2)
+    {
+      uint64_t begin = offsets[k], middle = offsets[k + 1], end = (k + 2 < offsets.size() ? offsets[k + 2] : offsets[k + 1]);
+      if(end == middle || middle == begin)   // a single (or empty) piece: copy
+      {
+        if(end > begin) { BWTM_CUDA(cudaMemcpyAsync(dst + begin, src + begin, (end - begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream)); }
+      }
+      else
+      {
+        size_t bytes = 0;
+        BWTM_CUDA(cub::DeviceMerge::MergeKeys(nullptr, bytes, src + begin, (int)(middle - begin), src + middle, (int)(end - middle), dst + begin, ::cuda::std::less<>{}, stream));
+        if(bytes > temp.bytes) { BWTM_TRY(temp.allocate(bytes)); }
+        BWTM_CUDA(cub::DeviceMerge::MergeKeys(temp.ptr, bytes, src + begin, (int)(middle - begin), src + middle, (int)(end - middle), dst + begin, ::cuda::std::less<>{}, stream));
+        count_launch(2);
+      }
+      next.push_back(end);
+    }
+    offsets.swap(next);
+    std::swap(src, dst);
+  }
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  *result = src;
+  return BWTM_OK;
+}
+
 template<class KeyT> struct NcclKey;
 template<> struct NcclKey<uint32_t> { static constexpr ncclDataType_t type = ncclUint32; };
 template<> struct NcclKey<uint64_t> { static constexpr ncclDataType_t type = ncclUint64; };
+
+struct PhaseClock   // BWTM_DEBUG=1: host wall clock per phase of the exchange, printed by every rank
+{
+  bool enabled; int rank; std::chrono::steady_clock::time_point last;
+  explicit PhaseClock(int r) : enabled(getenv("BWTM_DEBUG") != nullptr), rank(r), last(std::chrono::steady_clock::now()) {}
+  void mark(const char* name)
+  {
+    if(!enabled) { return; }
+    cudaDeviceSynchronize();
+    auto now = std::chrono::steady_clock::now();
+    fprintf(stderr, "bwtm[%d] %-22s %8.3f ms\n", rank, name, std::chrono::duration<double, std::milli>(now - last).count());
+    last = now;
+  }
+};
 
 template<class KeyT>
 static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
@@ -126,6 +178,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   const int G = comm->world, r = comm->rank;
   const uint64_t n_a = a->size, n_b = b->size, m_b = b->sequences;
   EventTimer timer(stream);
+  PhaseClock phase(r);
 
   // 1. search + local sort
   uint64_t seq_first = 0, seq_count = 0;
@@ -155,6 +208,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
     BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), local_n, bits, &sorted, stream));
   }
   timings->sort_seconds = timer.stop() * 1e-3;
+  phase.mark("walk + local sort");
 
   // 2. splitters: smallest p with p + #{keys < p} >= k (n_a + n_b) / G
   timer.start();
@@ -183,6 +237,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
       if(mid[k] + below[k] >= target[k]) { hi[k] = mid[k]; } else { lo[k] = mid[k] + 1; }
     }
   }
+  phase.mark("splitter search");
   std::vector<unsigned long long> splitter(G + 1, 0);
   for(int k = 0; k < P; k++) { splitter[k + 1] = std::max(lo[k], splitter[k]); }
   splitter[G] = n_a + 1;
@@ -224,6 +279,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   }
   timings->ra_values = all_values;
 
+  phase.mark("count matrix");
   // 4. all-to-all by A-position range, then 5. local sort of what arrived (G sorted pieces)
   DeviceBuffer received, received_alt;
   BWTM_TRY(received.allocate(std::max<uint64_t>(recv_total, 1) * sizeof(KeyT)));
@@ -236,19 +292,28 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   }
   BWTM_NCCL(api->GroupEnd());
   BWTM_CUDA(cudaStreamSynchronize(stream));
+  phase.mark("all-to-all");
   keys.release(); alt.release();
   KeyT* slice_keys = received.as<KeyT>();
   if(recv_total > 0 && G > 1)
   {
     BWTM_TRY(received_alt.allocate(recv_total * sizeof(KeyT)));
-    BWTM_TRY(sort_keys<KeyT>(received.as<KeyT>(), received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream));
+    if(recv_total < 0x7FFFFFFFull)
+    {
+      BWTM_TRY(merge_sorted_pieces<KeyT>(received.as<KeyT>(), received_alt.as<KeyT>(), recv_offset, stream, &slice_keys));
+    }
+    else { BWTM_TRY(sort_keys<KeyT>(received.as<KeyT>(), received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream)); }
   }
   timings->exchange_seconds = timer.stop() * 1e-3;
+  phase.mark("sort received");
 
   // 6. my slice of the merged BWT
   uint64_t a_lo = std::min<uint64_t>(splitter[r], n_a), a_hi = std::min<uint64_t>(splitter[r + 1], n_a);
   uint64_t begin = a_lo + b_lo, end = a_hi + b_lo + recv_total;
-  uint64_t slab = clamp_slab(options->slab_symbols, end - begin);
+  // A slice that fits one slab has its symbols and runs computed on all ranks at once; only the writer is
+  // chained. Without an explicit slab size the slab is stretched to the slice (up to the 2^31 item limit).
+  uint64_t slab = (options->slab_symbols == 0 && end - begin <= MAX_SLAB_SYMBOLS ? clamp_slab(end - begin, end - begin, true)
+                                                                                : clamp_slab(options->slab_symbols, end - begin));
   bool single_slab = (end - begin <= slab);
 
   DeviceBuffer merged, tile_j, control;
@@ -268,6 +333,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
     encode_ms += timer.stop();
   }
 
+  phase.mark("interleave + runs");
   // 7. the writer state comes from the previous slice and goes to the next one
   if(r > 0)
   {
@@ -304,6 +370,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   timings->encode_seconds = encode_ms * 1e-3;
   received.release(); received_alt.release(); merged.release();
 
+  phase.mark("chained writer");
   // 8. every rank gets the complete run-length BWT
   timer.start();
   unsigned long long mine[3] = { out.origin, ctl.out_size - out.origin, ctl.runs_total };
@@ -331,6 +398,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   timings->exchange_seconds += timer.stop() * 1e-3;
   (void)exchange_start;
 
+  phase.mark("gather slices");
   // 9. replica of the rank structure
   timer.start();
   uint64_t counts[SIGMA];
@@ -338,6 +406,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
   device_free(full.ptr);
   timings->index_seconds = timer.stop() * 1e-3;
+  phase.mark("index");
   return rc;
 }
 

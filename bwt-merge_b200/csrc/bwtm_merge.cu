@@ -493,10 +493,10 @@ int SlabEncoder::finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_
   return BWTM_OK;
 }
 
-uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total)
+uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total, bool allow_large)
 {
   if(slab_symbols == 0) { slab_symbols = 1ull << 30; }
-  slab_symbols = std::min(slab_symbols, (uint64_t)1 << 30);
+  slab_symbols = std::min(slab_symbols, allow_large ? MAX_SLAB_SYMBOLS : (uint64_t)1 << 30);
   slab_symbols = div_up(slab_symbols, TILE) * TILE;
   return std::min(slab_symbols, div_up(std::max(total, (uint64_t)1), TILE) * TILE);
 }

@@ -77,7 +77,9 @@ struct SlabEncoder
   int finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
 };
 
-uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total);
+// The run detection counts items in 32-bit ints: a slab holds fewer than 2^31 symbols.
+constexpr uint64_t MAX_SLAB_SYMBOLS = (1ull << 31) - (1ull << 16);
+uint64_t clamp_slab(uint64_t slab_symbols, uint64_t total, bool allow_large = false);
 int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cudaStream_t stream);
 
 // Symbols of a complete sequence (device, one comp per byte) -> index. Used by the fixture builder.
