@@ -484,7 +484,7 @@ int bwtm_merge_distributed(bwtm_comm* comm, bwtm_index* a, bwtm_index* b, const 
     *out = nullptr;
     uint64_t launches_before = bwtm_kernel_launches();
     auto start = std::chrono::steady_clock::now();
-    if(a->size < 0xFFFFFFFFull) { rc = merge_distributed_impl<uint32_t>(comm, a, b, options, out, &local); }
+    if(a->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr) { rc = merge_distributed_impl<uint32_t>(comm, a, b, options, out, &local); }
     else { rc = merge_distributed_impl<uint64_t>(comm, a, b, options, out, &local); }
     cudaDeviceSynchronize();
     local.total_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();

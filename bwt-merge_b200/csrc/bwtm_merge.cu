@@ -15,6 +15,7 @@
 //     exact byte offset.
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include <cub/cub.cuh>
@@ -723,7 +724,8 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
 int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
                 bwtm_index** result, bwtm_timings* timings)
 {
-  if(a->size < 0xFFFFFFFFull) { return merge_impl<uint32_t>(a, b, options, result, timings); }
+  // BWTM_FORCE_WIDE=1 runs the 64-bit key and position paths on small inputs (tests).
+  if(a->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr) { return merge_impl<uint32_t>(a, b, options, result, timings); }
   return merge_impl<uint64_t>(a, b, options, result, timings);
 }
 

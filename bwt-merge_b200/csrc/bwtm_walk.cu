@@ -317,7 +317,7 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
     k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
       device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
   }
-  else if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull)
+  else if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr)
   {
     BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, counters.as<WalkCounters>(), sms, stream)));
   }

@@ -201,3 +201,74 @@ def test_config1_shape_against_reference_binary(oracle, tmp_path):
                            "-r", "8", "-d", str(tmp_path), fa, fb, fm], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
     ref_chars = np.fromfile(fm, dtype=np.uint8)
     assert np.array_equal(synth.comps_to_chars(M.extract()), ref_chars)
+
+
+def _variable_reads(rng, genome, n, lo, hi):
+    reads = []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi + 1)); s = int(rng.integers(0, len(genome) - L + 1))
+        reads.append(genome[s:s + L].copy())
+    return reads
+
+
+def test_variable_length_sequences(oracle):
+    """Sequences of very different lengths (1..400): lanes of a warp finish at different times and refill."""
+    rng = np.random.default_rng(5)
+    g = synth.genome(3000, 42)
+    ra = _variable_reads(rng, g, 300, 1, 400); rb = _variable_reads(rng, g, 257, 1, 400)
+    A, B = oracle.from_comps(oracle.bwt_of_reads(ra)), oracle.from_comps(oracle.bwt_of_reads(rb))
+    want = oracle.merge(A, B)
+    DA, DB = FMI.from_rle(A.rle()), FMI.from_rle(B.rle())
+    assert np.array_equal(bwtm_b200.rank_array(DA, DB), np.sort(oracle.build_ra_walk(A, B)))
+    M = FMI.merge(DA, DB)
+    assert np.array_equal(M.rle(), want.rle())
+    assert np.array_equal(M.extract(), oracle.bwt_of_reads(ra + rb))
+
+
+@pytest.mark.parametrize("na,nb", [(1, 400), (400, 1), (1, 1), (3, 2)])
+def test_unbalanced_collections(oracle, na, nb):
+    ra, bwt_a = make_collection(oracle, 2000, na, 80, 0.01, 42, 1)
+    rb, bwt_b = make_collection(oracle, 2000, nb, 80, 0.01, 42, 2)
+    A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+    M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()))
+    assert np.array_equal(M.rle(), oracle.merge(A, B).rle())
+
+
+def test_wide_key_and_position_paths(oracle, monkeypatch):
+    """The 64-bit key / position instantiations (used when a BWT has >= 2^32 symbols) on small inputs."""
+    monkeypatch.setenv("BWTM_FORCE_WIDE", "1")
+    for shape in ("reads", "noisy_N", "repeats"):
+        ra, bwt_a, rb, bwt_b = collections(oracle, shape)
+        A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+        p = MergeParameters(); p.slab_symbols = 4096
+        M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+        assert np.array_equal(M.rle(), oracle.merge(A, B).rle()), shape
+
+
+def test_superblock_boundary():
+    """More than 2^25 symbols per input: several superblocks of the rank structure; merge == direct build."""
+    G, n, L, thr = 3_000_000, 400_000, 100, synth.error_threshold(0.01)
+    A = FMI.synthetic(G, 42, L, thr, [(1, n)]); B = FMI.synthetic(G, 42, L, thr, [(2, n // 2)])
+    assert A.size() > (1 << 25)
+    AB = FMI.synthetic(G, 42, L, thr, [(1, n), (2, n // 2)])
+    pats = [p for p in synth.patterns(synth.genome(G, 42), 500, 24, 3)]
+    pre = A.count(pats) + B.count(pats)
+    M = FMI.merge(A, B)
+    assert np.array_equal(M.rle(), AB.rle())
+    assert np.array_equal(M.count(pats), pre) and pre.sum() > 0
+
+
+def test_invalid_inputs_fail_loudly(oracle):
+    with pytest.raises(bwtm_b200.BwtmError):
+        FMI.from_rle(np.zeros(0, np.uint8))
+    ra, bwt_a = make_collection(oracle, 500, 20, 30, 0.0, 42, 1)
+    A = oracle.from_comps(bwt_a)
+    with pytest.raises(bwtm_b200.BwtmError):          # wrong expected counts
+        FMI.from_rle(A.rle(), expected_counts=A.counts() + np.uint64(1))
+    # a "BWT" without endmarkers cannot be inserted
+    with pytest.raises(bwtm_b200.BwtmError):
+        FMI.merge(FMI.from_rle(A.rle()), FMI.from_comps(np.full(100, 2, np.uint8)))
+    # a sequence whose walks do not cover it (not a BWT of a collection) is rejected, not mis-merged
+    bogus = np.concatenate([np.zeros(3, np.uint8), np.full(50, 1, np.uint8), np.full(50, 2, np.uint8)])
+    with pytest.raises(bwtm_b200.BwtmError):
+        FMI.merge(FMI.from_rle(A.rle()), FMI.from_comps(bogus))
