@@ -181,12 +181,15 @@ __device__ __forceinline__ uint32_t write_run(uint8_t* __restrict__ out, uint64_
   return (uint32_t)(pos - offset);
 }
 
-// Sequential glue between slabs: the RunBuffer state (pending maximal run) and Run::write for it.
+// Sequential glue between slabs (and GPU slices): the RunBuffer state (utils.h:121-142). The pending run
+// absorbs the slab's first run when the symbols agree; it is written as soon as the slab shows that it
+// has ended; the slab's last run becomes the new pending run. The runs in between, [1, m - 1), never
+// depend on the pending run: they are the parallel part.
 __global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ len,
                          uint64_t m, uint8_t* __restrict__ out, int finish)
 {
   if(blockIdx.x != 0 || threadIdx.x != 0) { return; }
-  ctl->start = 0; ctl->count = 0; ctl->n_short = 0; ctl->n_long = 0; ctl->long_bytes = 0;
+  ctl->start = 1; ctl->count = 0; ctl->n_short = 0; ctl->n_long = 0; ctl->long_bytes = 0;
   if(finish)
   {
     if(ctl->carry_len > 0)
@@ -197,20 +200,26 @@ __global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, co
     ctl->slab_base = ctl->out_size;
     return;
   }
-  bool merged = (ctl->carry_len > 0 && sym[0] == ctl->carry_sym);
-  if(merged && m == 1) { ctl->carry_len += len[0]; ctl->start = 1; ctl->slab_base = ctl->out_size; return; }
-  if(merged)
+  if(m > 0)
   {
-    ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len + len[0]);
-    ctl->runs_total++; ctl->start = 1;
+    if(ctl->carry_len > 0 && sym[0] == ctl->carry_sym) { ctl->carry_len += len[0]; }
+    else
+    {
+      if(ctl->carry_len > 0)
+      {
+        ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
+        ctl->runs_total++;
+      }
+      ctl->carry_sym = sym[0]; ctl->carry_len = len[0];
+    }
+    if(m > 1)
+    {
+      ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
+      ctl->runs_total++;
+      ctl->carry_sym = sym[m - 1]; ctl->carry_len = len[m - 1];
+      ctl->count = m - 2;
+    }
   }
-  else if(ctl->carry_len > 0)
-  {
-    ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
-    ctl->runs_total++;
-  }
-  ctl->carry_sym = sym[m - 1]; ctl->carry_len = len[m - 1];
-  ctl->count = (m - 1) - ctl->start;
   ctl->slab_base = ctl->out_size;
 }
 
@@ -222,7 +231,7 @@ struct RunClass   // 1 in the low word for a short run, 1 in the high word for a
   }
 };
 
-__global__ void enc_collect_long(EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+__global__ void enc_collect_long(unsigned long long* __restrict__ stats, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
                                  uint64_t count, uint32_t* __restrict__ long_list)
 {
   uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -233,8 +242,8 @@ __global__ void enc_collect_long(EncodeControl* ctl, const uint32_t* __restrict_
   if(is_long) { long_list[s >> 32] = (uint32_t)k; }
   if(k == count - 1)
   {
-    ctl->n_short = (s & 0xFFFFFFFFull) + (is_long ? 0 : 1);
-    ctl->n_long = (s >> 32) + (is_long ? 1 : 0);
+    stats[0] = (s & 0xFFFFFFFFull) + (is_long ? 0 : 1);   // short runs of the parallel part
+    stats[1] = (s >> 32) + (is_long ? 1 : 0);             // long runs
   }
 }
 
@@ -250,15 +259,16 @@ __device__ __forceinline__ uint32_t natural_bytes(uint32_t length)   // length >
   return 1u + bytecode_length((uint64_t)length - MAX_RUN);
 }
 
-// Transducer tile maps: bytes produced by the tile's long runs for each of the 64 residues of "bytes
-// produced by earlier long runs", with a checkpoint every LONG_SUB runs.
+// Transducer tile maps: bytes produced by the tile's long runs for each of the 64 residues q of
+// (offset of the parallel part + bytes of its earlier long runs) mod 64, with a checkpoint every LONG_SUB
+// runs. A long run preceded by `before` short runs starts at offset residue (before + q) mod 64, so the maps
+// do not depend on where the slab lands in the output: they are computed before the writer state is known.
 __global__ void __launch_bounds__(64)
-enc_tile_maps(const EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+enc_tile_maps(const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
               const uint32_t* __restrict__ long_list, uint64_t n_long, uint32_t* __restrict__ tile_bytes,
               uint16_t* __restrict__ checkpoints)
 {
   __shared__ uint32_t s_len[LONG_SUB], s_nat[LONG_SUB], s_before[LONG_SUB];
-  uint32_t base_state = (uint32_t)(ctl->slab_base & 63u);
   uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
   uint64_t last = (first + LONG_TILE < n_long ? first + LONG_TILE : n_long);
   uint32_t p = threadIdx.x;
@@ -272,7 +282,7 @@ enc_tile_maps(const EncodeControl* ctl, const uint32_t* __restrict__ len, const 
       uint32_t idx = long_list[chunk + threadIdx.x];
       uint32_t length = len[idx];
       s_len[threadIdx.x] = length; s_nat[threadIdx.x] = natural_bytes(length);
-      s_before[threadIdx.x] = base_state + (uint32_t)scan[idx];
+      s_before[threadIdx.x] = (uint32_t)scan[idx];
     }
     __syncthreads();
     int count = (int)(last - chunk < (uint64_t)LONG_SUB ? last - chunk : (uint64_t)LONG_SUB);
@@ -285,15 +295,16 @@ enc_tile_maps(const EncodeControl* ctl, const uint32_t* __restrict__ len, const 
   tile_bytes[(uint64_t)blockIdx.x * 64 + threadIdx.x] = p - threadIdx.x;
 }
 
-// Composition of the tile maps in order; the maps are staged through shared memory so that every
-// dependent step is a shared-memory lookup.
+// Composition of the tile maps in order, starting from the residue of the slab's output offset; the maps
+// are staged through shared memory so that every dependent step is a shared-memory lookup.
 __global__ void __launch_bounds__(256)
 enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint64_t tiles,
-              unsigned long long* __restrict__ tile_entry)
+              unsigned long long n_short, unsigned long long n_long, unsigned long long* __restrict__ tile_entry)
 {
   __shared__ uint32_t staged[SCAN_CHUNK * 64];
   __shared__ unsigned long long entries[SCAN_CHUNK];
   __shared__ unsigned long long carried;
+  const uint32_t base = (uint32_t)(ctl->slab_base & 63u);
   if(threadIdx.x == 0) { carried = 0; }
   __syncthreads();
   for(uint64_t first = 0; first < tiles; first += SCAN_CHUNK)
@@ -304,7 +315,7 @@ enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint6
     if(threadIdx.x == 0)
     {
       unsigned long long p = carried;
-      for(uint64_t t = 0; t < count; t++) { entries[t] = p; p += staged[t * 64 + (p & 63u)]; }
+      for(uint64_t t = 0; t < count; t++) { entries[t] = p; p += staged[t * 64 + ((base + (uint32_t)p) & 63u)]; }
       carried = p;
     }
     __syncthreads();
@@ -313,8 +324,9 @@ enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint6
   }
   if(threadIdx.x == 0)
   {
+    ctl->n_short = n_short; ctl->n_long = n_long;
     ctl->long_bytes = carried;
-    ctl->out_size = ctl->slab_base + ctl->n_short + carried;
+    ctl->out_size = ctl->slab_base + n_short + carried;
     ctl->runs_total += ctl->count;
   }
 }
@@ -332,7 +344,7 @@ __global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __res
   uint64_t last = (first + LONG_SUB < n_long ? first + LONG_SUB : n_long);
   uint32_t base_state = (uint32_t)(ctl->slab_base & 63u);
   unsigned long long entry = tile_entry[first / LONG_TILE];
-  unsigned long long p = entry + checkpoints[sub * 64 + (entry & 63u)];
+  unsigned long long p = entry + checkpoints[sub * 64 + ((base_state + (uint32_t)entry) & 63u)];
   for(uint64_t k = first; k < last; k++)
   {
     uint32_t idx = long_list[k];
@@ -387,7 +399,7 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   uint64_t max_long_tiles = div_up(max_long, LONG_TILE);
   BWTM_TRY(run_sym.allocate(max_symbols));
   BWTM_TRY(run_len.allocate(max_symbols * sizeof(uint32_t)));
-  BWTM_TRY(num_runs.allocate(sizeof(uint64_t)));
+  BWTM_TRY(num_runs.allocate(4 * sizeof(uint64_t)));
   BWTM_TRY(scan.allocate(max_symbols * sizeof(unsigned long long)));
   BWTM_TRY(long_list.allocate(max_long * sizeof(uint32_t)));
   BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
@@ -406,14 +418,15 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   return BWTM_OK;
 }
 
-// K3: maximal runs of `symbols` consecutive symbols.
+// K3 and the state-free half of K5: maximal runs of `symbols` consecutive symbols, and for the runs
+// [1, m - 1) the short/long scan, the compacted long runs and their transducer tile maps.
 int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream)
 {
-  detected_runs = 0;
+  detected_runs = 0; part_count = 0; part_short = 0; part_long = 0;
   if(symbols == 0) { return BWTM_OK; }
   if(symbols > max_symbols) { set_error("slab of %llu symbols exceeds the encoder capacity", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
   size_t temp_bytes = cub_temp.bytes;
-  BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, sizeof(uint64_t), stream));
+  BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, 4 * sizeof(uint64_t), stream));
   BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(cub_temp.ptr, temp_bytes, d_symbols, run_sym.as<uint8_t>(),
                                                 run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)symbols, stream));
   count_launch(3);
@@ -422,56 +435,57 @@ int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t
   BWTM_CUDA(cudaStreamSynchronize(stream));
   if(m == 0) { set_error("run-length encode produced no runs for %llu symbols", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
   detected_runs = m;
+  if(m < 3) { return BWTM_OK; }
+
+  uint64_t count = m - 2;
+  const uint32_t* len = run_len.as<uint32_t>() + 1;
+  unsigned long long* stats = num_runs.as<unsigned long long>() + 1;
+  cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes(len, RunClass());
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, classes, scan.as<unsigned long long>(), (int64_t)count, stream));
+  count_launch(2);
+  enc_collect_long<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(stats, len, scan.as<unsigned long long>(), count, long_list.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  unsigned long long host_stats[2] = { 0, 0 };
+  BWTM_CUDA(cudaMemcpyAsync(host_stats, stats, sizeof(host_stats), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  part_count = count; part_short = host_stats[0]; part_long = host_stats[1];
+  uint64_t long_tiles = div_up(part_long, LONG_TILE);
+  if(long_tiles > 0)
+  {
+    enc_tile_maps<<<(unsigned)long_tiles, 64, 0, stream>>>(len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), part_long,
+                                                           tile_bytes.as<uint32_t>(), checkpoints.as<uint16_t>());
+    BWTM_LAUNCH_CHECK();
+  }
   return BWTM_OK;
 }
 
-// K5: byte-exact Run::write of the detected runs, continuing from the state in d_control.
+// The state-dependent half of K5: continues from the writer state in d_control.
 int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
 {
   uint64_t m = detected_runs;
   if(m == 0) { return BWTM_OK; }
-  size_t temp_bytes = cub_temp.bytes;
   EncodeControl ctl;
   BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.out_size, stream));
+  // Upper bound of what this slab can add: two sequential runs, one byte per short run, 16 per long run.
+  BWTM_TRY(ensure_capacity(out, ctl.out_size + 512 + part_short + 16 * part_long, ctl.out_size, stream));
   enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_len.as<uint32_t>(), m, out->at_origin(), 0);
   BWTM_LAUNCH_CHECK();
-  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaStreamSynchronize(stream));
-  if(ctl.count == 0) { return BWTM_OK; }
+  if(part_count == 0) { return BWTM_OK; }
 
-  uint64_t count = ctl.count;
-  const uint8_t* sym = run_sym.as<uint8_t>() + ctl.start;
-  const uint32_t* len = run_len.as<uint32_t>() + ctl.start;
-  cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes(len, RunClass());
-  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, classes, scan.as<unsigned long long>(), (int64_t)count, stream));
-  count_launch(2);
-  enc_collect_long<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), count, long_list.as<uint32_t>());
-  BWTM_LAUNCH_CHECK();
-  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaStreamSynchronize(stream));
-  uint64_t n_long = ctl.n_long;
-  uint64_t long_tiles = div_up(n_long, LONG_TILE);
-  if(long_tiles > 0)
-  {
-    enc_tile_maps<<<(unsigned)long_tiles, 64, 0, stream>>>(d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), n_long,
-                                                           tile_bytes.as<uint32_t>(), checkpoints.as<uint16_t>());
-    BWTM_LAUNCH_CHECK();
-  }
-  enc_tile_scan<<<1, 256, 0, stream>>>(d_control, tile_bytes.as<uint32_t>(), long_tiles, tile_entry.as<unsigned long long>());
+  const uint8_t* sym = run_sym.as<uint8_t>() + 1;
+  const uint32_t* len = run_len.as<uint32_t>() + 1;
+  uint64_t long_tiles = div_up(part_long, LONG_TILE);
+  enc_tile_scan<<<1, 256, 0, stream>>>(d_control, tile_bytes.as<uint32_t>(), long_tiles, part_short, part_long, tile_entry.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
   if(long_tiles > 0)
   {
-    enc_long_offsets<<<(unsigned)div_up(div_up(n_long, LONG_SUB), 128), 128, 0, stream>>>(
-      d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), n_long,
+    enc_long_offsets<<<(unsigned)div_up(div_up(part_long, LONG_SUB), 128), 128, 0, stream>>>(
+      d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), part_long,
       tile_entry.as<unsigned long long>(), checkpoints.as<uint16_t>(), long_offset.as<uint32_t>());
     BWTM_LAUNCH_CHECK();
   }
-  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaStreamSynchronize(stream));
-  BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.slab_base, stream));
-  enc_write<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(d_control, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), count, out->at_origin());
+  enc_write<<<(unsigned)div_up(part_count, 256), 256, 0, stream>>>(d_control, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), part_count, out->at_origin());
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }

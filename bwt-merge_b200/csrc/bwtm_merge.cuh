@@ -67,7 +67,8 @@ struct SlabEncoder
 {
   uint64_t max_symbols;
   DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, cub_temp;
-  uint64_t detected_runs;   // result of detect()
+  uint64_t detected_runs;                       // result of detect(): maximal runs of the slab
+  uint64_t part_count, part_short, part_long;   // its parallel part, runs [1, m - 1)
   int init(uint64_t max_symbols, cudaStream_t stream);
   // K3: maximal runs of the slab; independent of the encoder state.
   int detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream);
