@@ -349,13 +349,17 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   timer.start();
   if(rc == BWTM_OK && end > begin)
   {
-    if(single_slab) { rc = encoder.write(&out, control.as<EncodeControl>(), stream); }
+    if(single_slab) { rc = encoder.advance(&out, control.as<EncodeControl>(), stream); }
     else
     {
       rc = interleave_range<KeyT>(a, b, slice_keys, b_lo, recv_total, begin, end, options->slab_symbols, &out,
                                   control.as<EncodeControl>(), false, &interleave_ms, &encode_ms, stream);
     }
   }
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  // The next slice only needs the state after this one: it goes out before the bytes are written.
+  if(r < G - 1) { BWTM_NCCL(api->Send(control.ptr, sizeof(EncodeControl), ncclUint8, r + 1, comm->comm, stream)); }
+  if(single_slab && end > begin) { rc = encoder.emit(&out, stream); }
   if(rc == BWTM_OK && r == G - 1)
   {
     if(!single_slab || end == begin) { rc = encoder.init(4096, stream); }
@@ -363,7 +367,6 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   }
   if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   if(single_slab) { encode_ms += timer.stop(); } else { timer.stop(); }
-  if(r < G - 1) { BWTM_NCCL(api->Send(control.ptr, sizeof(EncodeControl), ncclUint8, r + 1, comm->comm, stream)); }
   BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   timings->interleave_seconds = interleave_ms * 1e-3;

@@ -400,6 +400,7 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   BWTM_TRY(run_sym.allocate(max_symbols));
   BWTM_TRY(run_len.allocate(max_symbols * sizeof(uint32_t)));
   BWTM_TRY(num_runs.allocate(4 * sizeof(uint64_t)));
+  BWTM_TRY(placed.allocate(sizeof(EncodeControl)));
   BWTM_TRY(scan.allocate(max_symbols * sizeof(unsigned long long)));
   BWTM_TRY(long_list.allocate(max_long * sizeof(uint32_t)));
   BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
@@ -459,8 +460,10 @@ int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t
   return BWTM_OK;
 }
 
-// The state-dependent half of K5: continues from the writer state in d_control.
-int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+// The state-dependent half of K5, first step: consumes the writer state in d_control (pending run, output
+// offset) and leaves the state after this slab there. Cheap and sequential; the next slab or GPU slice
+// can start from d_control as soon as this returns (stream order).
+int SlabEncoder::advance(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
 {
   uint64_t m = detected_runs;
   if(m == 0) { return BWTM_OK; }
@@ -472,22 +475,36 @@ int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t
   enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_len.as<uint32_t>(), m, out->at_origin(), 0);
   BWTM_LAUNCH_CHECK();
   if(part_count == 0) { return BWTM_OK; }
-
-  const uint8_t* sym = run_sym.as<uint8_t>() + 1;
-  const uint32_t* len = run_len.as<uint32_t>() + 1;
   uint64_t long_tiles = div_up(part_long, LONG_TILE);
   enc_tile_scan<<<1, 256, 0, stream>>>(d_control, tile_bytes.as<uint32_t>(), long_tiles, part_short, part_long, tile_entry.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
-  if(long_tiles > 0)
+  BWTM_CUDA(cudaMemcpyAsync(placed.ptr, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToDevice, stream));
+  return BWTM_OK;
+}
+
+// Second step: writes the bytes of the parallel part at the offsets fixed by advance().
+int SlabEncoder::emit(OutputBuffer* out, cudaStream_t stream)
+{
+  if(detected_runs == 0 || part_count == 0) { return BWTM_OK; }
+  const EncodeControl* where = placed.as<EncodeControl>();
+  const uint8_t* sym = run_sym.as<uint8_t>() + 1;
+  const uint32_t* len = run_len.as<uint32_t>() + 1;
+  if(part_long > 0)
   {
     enc_long_offsets<<<(unsigned)div_up(div_up(part_long, LONG_SUB), 128), 128, 0, stream>>>(
-      d_control, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), part_long,
+      where, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), part_long,
       tile_entry.as<unsigned long long>(), checkpoints.as<uint16_t>(), long_offset.as<uint32_t>());
     BWTM_LAUNCH_CHECK();
   }
-  enc_write<<<(unsigned)div_up(part_count, 256), 256, 0, stream>>>(d_control, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), part_count, out->at_origin());
+  enc_write<<<(unsigned)div_up(part_count, 256), 256, 0, stream>>>(where, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), part_count, out->at_origin());
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
+}
+
+int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+{
+  BWTM_TRY(this->advance(out, d_control, stream));
+  return this->emit(out, stream);
 }
 
 int SlabEncoder::encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)

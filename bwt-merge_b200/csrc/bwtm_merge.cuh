@@ -66,13 +66,16 @@ struct EventTimer
 struct SlabEncoder
 {
   uint64_t max_symbols;
-  DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, cub_temp;
+  DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, placed, cub_temp;
   uint64_t detected_runs;                       // result of detect(): maximal runs of the slab
   uint64_t part_count, part_short, part_long;   // its parallel part, runs [1, m - 1)
   int init(uint64_t max_symbols, cudaStream_t stream);
   // K3: maximal runs of the slab; independent of the encoder state.
   int detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream);
-  // K5: writes the runs found by detect() continuing from the state in d_control.
+  // K5: writes the runs found by detect() continuing from the state in d_control. write = advance + emit:
+  // advance() moves the writer state past this slab (sequential, tiny), emit() writes the bytes.
+  int advance(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
+  int emit(OutputBuffer* out, cudaStream_t stream);
   int write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
   int encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
   int finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
