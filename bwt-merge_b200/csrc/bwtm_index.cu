@@ -160,40 +160,83 @@ k0_block_lengths(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t b
 }
 
 // Sets the plane bits of every run. Records must be zero-initialised.
+//
+// A CTA decodes K0_THREADS consecutive 64-byte blocks, i.e. one contiguous range of positions. When the
+// range fits, the three planes of the range are assembled in shared memory (shared atomics), the 16-byte
+// chunks that lie entirely inside the range are written with plain coalesced stores and only the first and
+// last chunk, which neighbouring CTAs may share, go through global atomics. Ranges that do not fit (very long
+// runs) fall back to global atomics for every word.
+constexpr int K0_PLANE_WORDS = 3072;   // 32-position chunks per CTA range held in shared memory
+
+__device__ __forceinline__ void set_run_bits(uint32_t* p0, uint32_t* p1, uint32_t* p2, uint64_t stride,
+                                             uint64_t first_chunk, uint32_t comp, uint64_t pos, uint64_t length, bool shared)
+{
+  uint64_t p = pos, remaining = length;
+  while(remaining > 0)
+  {
+    uint64_t index = ((p >> 5) - first_chunk) * stride;
+    uint32_t t = (uint32_t)(p & 31u);
+    uint32_t take = (uint32_t)(remaining < (uint64_t)(32 - t) ? remaining : (uint64_t)(32 - t));
+    uint32_t mask = low_mask((int)take) << t;
+    if(comp & 1u) { atomicOr(p0 + index, mask); }
+    if(comp & 2u) { atomicOr(p1 + index, mask); }
+    if(comp & 4u) { atomicOr(p2 + index, mask); }
+    p += take; remaining -= take;
+  }
+  (void)shared;
+}
+
 __global__ void __launch_bounds__(K0_THREADS)
 k0_fill_planes(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t blocks,
                const uint64_t* __restrict__ starts, uint32_t* __restrict__ record_words)
 {
   __shared__ __align__(16) uint8_t smem[K0_THREADS * K0_STRIDE];
+  __shared__ uint32_t planes[3][K0_PLANE_WORDS];
   uint64_t first_block = (uint64_t)blockIdx.x * K0_THREADS;
   stage_blocks(rle, first_block, rle_bytes, smem);
+
+  uint64_t last_block = (first_block + K0_THREADS < blocks ? first_block + K0_THREADS : blocks);
+  uint64_t range_begin = starts[first_block], range_end = starts[last_block];
+  uint64_t first_chunk = range_begin >> 5;
+  uint64_t chunks = (range_end > range_begin ? ((range_end - 1) >> 5) - first_chunk + 1 : 0);
+  bool staged = (chunks <= (uint64_t)K0_PLANE_WORDS);
+  if(staged)
+  {
+    for(uint64_t w = threadIdx.x; w < chunks; w += K0_THREADS) { planes[0][w] = 0; planes[1][w] = 0; planes[2][w] = 0; }
+  }
   __syncthreads();
 
   uint64_t block = first_block + threadIdx.x;
-  if(block >= blocks) { return; }
-  uint64_t begin = block * RLE_BLOCK;
-  int limit = (int)(rle_bytes - begin < (uint64_t)RLE_BLOCK ? rle_bytes - begin : (uint64_t)RLE_BLOCK);
-  uint64_t pos = starts[block];
-  decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
+  if(block < blocks)
   {
-    if(comp != 0)
+    uint64_t begin = block * RLE_BLOCK;
+    int limit = (int)(rle_bytes - begin < (uint64_t)RLE_BLOCK ? rle_bytes - begin : (uint64_t)RLE_BLOCK);
+    uint64_t pos = starts[block];
+    decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
     {
-      uint64_t p = pos, remaining = length;
-      while(remaining > 0)
+      if(comp != 0)
       {
-        uint64_t group = p >> 5;            // 32-position chunk
-        uint32_t t = (uint32_t)(p & 31u);
-        uint32_t take = (uint32_t)(remaining < (uint64_t)(32 - t) ? remaining : (uint64_t)(32 - t));
-        uint32_t mask = low_mask((int)take) << t;
-        uint32_t* chunk = record_words + group * 4;
-        if(comp & 1u) { atomicOr(chunk + 0, mask); }
-        if(comp & 2u) { atomicOr(chunk + 1, mask); }
-        if(comp & 4u) { atomicOr(chunk + 2, mask); }
-        p += take; remaining -= take;
+        if(staged) { set_run_bits(planes[0], planes[1], planes[2], 1, first_chunk, comp, pos, length, true); }
+        else { set_run_bits(record_words, record_words + 1, record_words + 2, 4, 0, comp, pos, length, false); }
       }
+      pos += length;
+    });
+  }
+  if(!staged) { return; }
+  __syncthreads();
+
+  for(uint64_t w = threadIdx.x; w < chunks; w += K0_THREADS)
+  {
+    uint32_t a = planes[0][w], b = planes[1][w], c = planes[2][w];
+    uint32_t* chunk = record_words + (first_chunk + w) * 4;
+    if(w > 0 && w + 1 < chunks) { *reinterpret_cast<uint4*>(chunk) = make_uint4(a, b, c, 0); }
+    else
+    {
+      if(a != 0) { atomicOr(chunk + 0, a); }
+      if(b != 0) { atomicOr(chunk + 1, b); }
+      if(c != 0) { atomicOr(chunk + 2, c); }
     }
-    pos += length;
-  });
+  }
 }
 
 // Per-record counts of comps 1..5 (positions beyond `size` hold comp 0 and are never counted).

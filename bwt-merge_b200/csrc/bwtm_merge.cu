@@ -682,6 +682,158 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   return rc;
 }
 
+// K1 and K2 overlapped. The walk is bound by random line requests and leaves most of the HBM bandwidth
+// idle; the radix sort is the opposite. B's sequences are walked in chunks on one stream (with a reduced
+// number of resident blocks per SM) while finished chunks are sorted and merged pairwise on a second
+// stream. The RA multiset does not depend on how B's sequences are split (fmi.cpp:355).
+template<class KeyT>
+static int walk_sort_pipelined(const bwtm_index* a, const bwtm_index* b, KeyT* keys, KeyT* alt, uint64_t n_b, int bits, int chunks,
+                               KeyT** sorted, bwtm_timings* timings)
+{
+  const uint64_t m = b->sequences;
+  const uint64_t counter_stride = div_up(walk_counters_bytes(), 64) * 64;
+  int walk_blocks = 6;
+  if(const char* env = getenv("BWTM_WALK_CTAS")) { walk_blocks = atoi(env); }
+
+  DeviceBuffer counters, cursor, sort_temp, merge_temp;
+  BWTM_TRY(counters.allocate(counter_stride * chunks));
+  BWTM_TRY(cursor.allocate(sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, counter_stride * chunks, 0));
+  BWTM_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned long long), 0));
+  uint64_t max_chunk = std::min(n_b, (n_b / chunks) * 2 + (1 << 20));
+  size_t sort_bytes = 0, merge_bytes = 0;
+  {
+    cub::DoubleBuffer<KeyT> probe(keys, alt);
+    BWTM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, probe, (int64_t)n_b, 0, bits, 0));
+    BWTM_CUDA(cub::DeviceMerge::MergeKeys(nullptr, merge_bytes, keys, (int)std::min<uint64_t>(n_b, 0x3FFFFFFF), keys, (int)std::min<uint64_t>(n_b, 0x3FFFFFFF), alt, ::cuda::std::less<>{}, 0));
+  }
+  (void)max_chunk;
+  BWTM_TRY(sort_temp.allocate(sort_bytes)); BWTM_TRY(merge_temp.allocate(merge_bytes));
+
+  std::vector<unsigned char> host_counters(counter_stride * chunks, 0);
+  std::vector<unsigned long long> host_cursor(chunks, 0);
+  unsigned long long* pinned = nullptr;
+  BWTM_CUDA(cudaMallocHost(&pinned, sizeof(unsigned long long) * chunks + counter_stride * chunks));
+  unsigned char* pinned_counters = reinterpret_cast<unsigned char*>(pinned + chunks);
+
+  cudaStream_t s_walk = nullptr, s_sort = nullptr;
+  cudaEvent_t ready = nullptr, begin = nullptr, walked_all = nullptr, done = nullptr;
+  std::vector<cudaEvent_t> walked(chunks, nullptr);
+  int rc = BWTM_OK;
+  auto cleanup = [&]()
+  {
+    if(s_walk) { cudaStreamSynchronize(s_walk); cudaStreamDestroy(s_walk); }
+    if(s_sort) { cudaStreamSynchronize(s_sort); cudaStreamDestroy(s_sort); }
+    for(cudaEvent_t e : walked) { if(e) { cudaEventDestroy(e); } }
+    for(cudaEvent_t e : { ready, begin, walked_all, done }) { if(e) { cudaEventDestroy(e); } }
+    if(pinned) { cudaFreeHost(pinned); }
+  };
+#define BWTM_PIPE(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { rc = cuda_failed(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while(0)
+#define BWTM_PIPE_TRY(call) do { rc = (call); if(rc != BWTM_OK) { cleanup(); return rc; } } while(0)
+
+  BWTM_PIPE(cudaStreamCreateWithFlags(&s_walk, cudaStreamNonBlocking));
+  BWTM_PIPE(cudaStreamCreateWithFlags(&s_sort, cudaStreamNonBlocking));
+  BWTM_PIPE(cudaEventCreate(&ready)); BWTM_PIPE(cudaEventCreate(&begin));
+  BWTM_PIPE(cudaEventCreate(&walked_all)); BWTM_PIPE(cudaEventCreate(&done));
+  for(int c = 0; c < chunks; c++) { BWTM_PIPE(cudaEventCreateWithFlags(&walked[c], cudaEventDisableTiming)); }
+  BWTM_PIPE(cudaEventRecord(ready, 0));
+  BWTM_PIPE(cudaStreamWaitEvent(s_walk, ready, 0)); BWTM_PIPE(cudaStreamWaitEvent(s_sort, ready, 0));
+  BWTM_PIPE(cudaEventRecord(begin, s_walk));
+
+  // All walks are enqueued up front; each leaves its end offset and counters in pinned memory.
+  for(int c = 0; c < chunks; c++)
+  {
+    uint64_t first = (uint64_t)(((__uint128_t)m * c) / chunks), last = (uint64_t)(((__uint128_t)m * (c + 1)) / chunks);
+    if(last > first)
+    {
+      BWTM_PIPE_TRY(walk_sequences_async<KeyT>(a, b, first, last - 1, keys, n_b, counters.as<unsigned char>() + counter_stride * c,
+                                               cursor.as<unsigned long long>(), walk_blocks, s_walk));
+    }
+    BWTM_PIPE(cudaMemcpyAsync(pinned + c, cursor.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_walk));
+    BWTM_PIPE(cudaMemcpyAsync(pinned_counters + counter_stride * c, counters.as<unsigned char>() + counter_stride * c, counter_stride,
+                              cudaMemcpyDeviceToHost, s_walk));
+    BWTM_PIPE(cudaEventRecord(walked[c], s_walk));
+  }
+  BWTM_PIPE(cudaEventRecord(walked_all, s_walk));
+  timings->walk_kernel_launches = chunks;
+
+  // Sort every chunk as it arrives; merge equal-level neighbours (a binary counter of sorted runs).
+  struct SortedRun { uint64_t begin, end; int level; KeyT* where; };
+  std::vector<SortedRun> runs;
+  uint64_t previous_end = 0;
+  for(int c = 0; c < chunks; c++)
+  {
+    BWTM_PIPE(cudaEventSynchronize(walked[c]));
+    if(walk_counters_check(pinned_counters + counter_stride * c) || pinned[c] > n_b)
+    {
+      set_error("the rank array has more than %llu values: the inserted BWT is not a valid multi-string BWT", (unsigned long long)n_b);
+      rc = BWTM_ERR_INTERNAL; cleanup(); return rc;
+    }
+    uint64_t chunk_begin = previous_end, chunk_end = pinned[c];
+    previous_end = chunk_end;
+    if(chunk_end == chunk_begin) { continue; }
+    cub::DoubleBuffer<KeyT> buffers(keys + chunk_begin, alt + chunk_begin);
+    size_t bytes = sort_temp.bytes;
+    BWTM_PIPE(cub::DeviceRadixSort::SortKeys(sort_temp.ptr, bytes, buffers, (int64_t)(chunk_end - chunk_begin), 0, bits, s_sort));
+    count_launch((uint64_t)(2 + (bits + 7) / 8));
+    KeyT* base = (buffers.Current() == keys + chunk_begin ? keys : alt);
+    runs.push_back({ chunk_begin, chunk_end, 0, base });
+    while(runs.size() >= 2 && runs[runs.size() - 1].level == runs[runs.size() - 2].level)
+    {
+      SortedRun right = runs.back(); runs.pop_back();
+      SortedRun left = runs.back(); runs.pop_back();
+      KeyT* target = (left.where == keys ? alt : keys);
+      if(right.where != left.where)   // different pass parity cannot happen (same bit count), but stay safe
+      {
+        BWTM_PIPE(cudaMemcpyAsync(left.where + right.begin, right.where + right.begin, (right.end - right.begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, s_sort));
+      }
+      size_t mb = merge_temp.bytes;
+      BWTM_PIPE(cub::DeviceMerge::MergeKeys(merge_temp.ptr, mb, left.where + left.begin, (int)(left.end - left.begin),
+                                            left.where + right.begin, (int)(right.end - right.begin), target + left.begin,
+                                            ::cuda::std::less<>{}, s_sort));
+      count_launch(2);
+      runs.push_back({ left.begin, right.end, left.level + 1, target });
+    }
+  }
+  // Leftover runs of different levels (chunk count not a power of two, or empty chunks): merge right to left.
+  while(runs.size() >= 2)
+  {
+    SortedRun right = runs.back(); runs.pop_back();
+    SortedRun left = runs.back(); runs.pop_back();
+    KeyT* target = (left.where == keys ? alt : keys);
+    if(right.where != left.where)
+    {
+      BWTM_PIPE(cudaMemcpyAsync(left.where + right.begin, right.where + right.begin, (right.end - right.begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, s_sort));
+    }
+    size_t mb = merge_temp.bytes;
+    BWTM_PIPE(cub::DeviceMerge::MergeKeys(merge_temp.ptr, mb, left.where + left.begin, (int)(left.end - left.begin),
+                                          left.where + right.begin, (int)(right.end - right.begin), target + left.begin,
+                                          ::cuda::std::less<>{}, s_sort));
+    count_launch(2);
+    runs.push_back({ left.begin, right.end, std::max(left.level, right.level) + 1, target });
+  }
+  BWTM_PIPE(cudaEventRecord(done, s_sort));
+  BWTM_PIPE(cudaEventSynchronize(done));
+  float walk_ms = 0.0f, total_ms = 0.0f;
+  cudaEventElapsedTime(&walk_ms, begin, walked_all);
+  cudaEventElapsedTime(&total_ms, begin, done);
+  timings->search_seconds = walk_ms * 1e-3;
+  timings->sort_seconds = std::max(0.0f, total_ms - walk_ms) * 1e-3;   // what the overlap did not hide
+  timings->ra_values = previous_end;
+  *sorted = (runs.empty() ? keys : runs.back().where);
+  uint64_t emitted = previous_end;
+  cleanup();
+#undef BWTM_PIPE
+#undef BWTM_PIPE_TRY
+  if(emitted != n_b)
+  {
+    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
+              (unsigned long long)emitted, (unsigned long long)n_b);
+    return BWTM_ERR_INTERNAL;
+  }
+  return BWTM_OK;
+}
+
 template<class KeyT>
 static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
                       bwtm_index** result, bwtm_timings* timings)
@@ -693,23 +845,36 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   BWTM_TRY(alt.allocate(n_b * sizeof(KeyT)));
 
   EventTimer timer(stream);
-  timer.start();
-  uint64_t emitted = 0;
-  BWTM_TRY(walk_sequences<KeyT>(a, b, 0, b->sequences - 1, keys.as<KeyT>(), n_b, &emitted, stream));
-  timings->search_seconds = timer.stop() * 1e-3;
-  timings->walk_kernel_launches = 1;
-  if(emitted != n_b)
-  {
-    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
-              (unsigned long long)emitted, (unsigned long long)n_b);
-    return BWTM_ERR_INTERNAL;
-  }
-  timings->ra_values = emitted;
-
-  timer.start();
   KeyT* sorted = nullptr;
-  BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream));
-  timings->sort_seconds = timer.stop() * 1e-3;
+  // Overlapping the walk with the sort of finished chunks is implemented (walk_sort_pipelined) but off by
+  // default: on B200 the two kernels slow each other down by as much as the overlap hides (config 2: 93 ms
+  // either way, profiles/r01_pipeline_sweep.txt). BWTM_PIPELINE_CHUNKS=<n> turns it on.
+  int chunks = 1;
+  if(const char* env = getenv("BWTM_PIPELINE_CHUNKS")) { chunks = atoi(env); }
+  uint64_t pipeline_min = 1ull << 26;   // below this the overlap does not pay for the extra launches
+  if(const char* env = getenv("BWTM_PIPELINE_MIN")) { pipeline_min = strtoull(env, nullptr, 10); }
+  if(chunks > 1 && n_b >= pipeline_min && n_b < 0x7FFFFFFFull && b->sequences >= (uint64_t)chunks)
+  {
+    BWTM_TRY(walk_sort_pipelined<KeyT>(a, b, keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), chunks, &sorted, timings));
+  }
+  else
+  {
+    timer.start();
+    uint64_t emitted = 0;
+    BWTM_TRY(walk_sequences<KeyT>(a, b, 0, b->sequences - 1, keys.as<KeyT>(), n_b, &emitted, stream));
+    timings->search_seconds = timer.stop() * 1e-3;
+    timings->walk_kernel_launches = 1;
+    if(emitted != n_b)
+    {
+      set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
+                (unsigned long long)emitted, (unsigned long long)n_b);
+      return BWTM_ERR_INTERNAL;
+    }
+    timings->ra_values = emitted;
+    timer.start();
+    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream));
+    timings->sort_seconds = timer.stop() * 1e-3;
+  }
   if(sorted == keys.as<KeyT>()) { alt.release(); } else { keys.release(); }
 
   {

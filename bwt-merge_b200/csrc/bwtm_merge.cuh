@@ -11,6 +11,15 @@ template<class KeyT>
 int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                    KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream);
 
+// K1 without waiting: enqueues the walk on `stream`; RA values are appended at *cursor, which consecutive
+// launches may share. `counters` (walk_counters_bytes() zeroed bytes) is private to the launch.
+template<class KeyT>
+int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                         KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor,
+                         int max_blocks_per_sm, cudaStream_t stream);
+uint64_t walk_counters_bytes();
+int walk_counters_check(const void* host_copy);   // non-zero: the output buffer overflowed
+
 // K2. Radix sort on the low `bits` bits; *sorted points into d_keys or d_alt.
 template<class KeyT>
 int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream);

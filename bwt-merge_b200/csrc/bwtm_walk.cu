@@ -31,15 +31,15 @@ constexpr int WALK_STAGE   = 256;   // staged RA values per warp
 
 struct WalkCounters
 {
-  unsigned long long next_sequence;   // relative to seq_begin
-  unsigned long long emitted;
+  unsigned long long next_sequence;   // relative to seq_begin, per launch
+  unsigned long long emitted;         // output cursor (may be shared by consecutive launches: `cursor`)
   int                overflow;
 };
 
 template<class KeyT>
 __global__ void __launch_bounds__(WALK_THREADS, 4)
 k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
-        KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters)
+        KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor)
 {
   __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
   __shared__ uint64_t c_a[8], c_b[8];
@@ -87,7 +87,7 @@ k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
     {
       __syncwarp();
       unsigned long long base = 0;
-      if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+      if(lane == 0) { base = atomicAdd(cursor, (unsigned long long)fill); }
       base = __shfl_sync(FULL, base, 0);
       if(base + fill <= capacity)
       {
@@ -126,7 +126,7 @@ k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
   {
     __syncwarp();
     unsigned long long base = 0;
-    if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+    if(lane == 0) { base = atomicAdd(cursor, (unsigned long long)fill); }
     base = __shfl_sync(FULL, base, 0);
     if(base + fill <= capacity)
     {
@@ -174,7 +174,7 @@ __device__ __forceinline__ uint32_t coop_record_rank(const uint4& q, uint32_t of
 template<class KeyT, class PosT>
 __global__ void __launch_bounds__(WALK_THREADS, 8)
 k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
-             KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters)
+             KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor)
 {
   __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
   __shared__ PosT c_a[8], c_b[8];
@@ -235,7 +235,7 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
     {
       __syncwarp();
       unsigned long long base = 0;
-      if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+      if(lane == 0) { base = atomicAdd(cursor, (unsigned long long)fill); }
       base = __shfl_sync(FULL, base, 0);
       if(base + fill <= capacity)
       {
@@ -273,7 +273,7 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
   {
     __syncwarp();
     unsigned long long base = 0;
-    if(lane == 0) { base = atomicAdd(&(counters->emitted), (unsigned long long)fill); }
+    if(lane == 0) { base = atomicAdd(cursor, (unsigned long long)fill); }
     base = __shfl_sync(FULL, base, 0);
     if(base + fill <= capacity)
     {
@@ -285,16 +285,51 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
 
 template<class KeyT, class PosT>
 static int launch_coop(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
-                       KeyT* d_out, uint64_t capacity, WalkCounters* counters, int sms, cudaStream_t stream)
+                       KeyT* d_out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor,
+                       int sms, int max_blocks_per_sm, cudaStream_t stream)
 {
   int per_sm = 0;
   BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_coop<KeyT, PosT>, WALK_THREADS, 0));
   if(per_sm < 1) { per_sm = 1; }
+  if(max_blocks_per_sm > 0 && per_sm > max_blocks_per_sm) { per_sm = max_blocks_per_sm; }
   uint64_t sequences = seq_last + 1 - seq_first;
   uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS / COOP_LANES));
   k1_walk_coop<KeyT, PosT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
-    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters);
+    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters, cursor);
   return BWTM_OK;
+}
+
+// Enqueues one walk over the sequences [seq_first, seq_last] on `stream` without waiting for it.
+// `counters` must be zeroed; RA values are appended at *cursor (shared by consecutive launches).
+template<class KeyT>
+int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                         KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor,
+                         int max_blocks_per_sm, cudaStream_t stream)
+{
+  int device = 0, sms = 0;
+  BWTM_CUDA(cudaGetDevice(&device));
+  BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr)
+  {
+    BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream)));
+  }
+  else
+  {
+    BWTM_TRY((launch_coop<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream)));
+  }
+  BWTM_LAUNCH_CHECK();
+  return BWTM_OK;
+}
+
+template int walk_sequences_async<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, void*, unsigned long long*, int, cudaStream_t);
+template int walk_sequences_async<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, void*, unsigned long long*, int, cudaStream_t);
+
+uint64_t walk_counters_bytes() { return sizeof(WalkCounters); }
+
+int walk_counters_check(const void* host_copy)
+{
+  const WalkCounters* c = static_cast<const WalkCounters*>(host_copy);
+  return c->overflow;
 }
 
 template<class KeyT>
@@ -308,6 +343,7 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   uint64_t sequences = seq_last + 1 - seq_first;
+  unsigned long long* cursor = &(counters.as<WalkCounters>()->emitted);
   const char* variant = getenv("BWTM_WALK");
   if(variant != nullptr && variant[0] == '1')   // thread-per-walker form, kept for A/B measurements
   {
@@ -315,17 +351,13 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
     if(per_sm < 1) { per_sm = 1; }
     uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS));
     k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
-      device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>());
-  }
-  else if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr)
-  {
-    BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, counters.as<WalkCounters>(), sms, stream)));
+      device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>(), cursor);
+    BWTM_LAUNCH_CHECK();
   }
   else
   {
-    BWTM_TRY((launch_coop<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, counters.as<WalkCounters>(), sms, stream)));
+    BWTM_TRY(walk_sequences_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters.ptr, cursor, 0, stream));
   }
-  BWTM_LAUNCH_CHECK();
 
   WalkCounters host;
   BWTM_CUDA(cudaMemcpyAsync(&host, counters.ptr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, stream));

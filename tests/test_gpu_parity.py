@@ -272,3 +272,21 @@ def test_invalid_inputs_fail_loudly(oracle):
     bogus = np.concatenate([np.zeros(3, np.uint8), np.full(50, 1, np.uint8), np.full(50, 2, np.uint8)])
     with pytest.raises(bwtm_b200.BwtmError):
         FMI.merge(FMI.from_rle(A.rle()), FMI.from_comps(bogus))
+
+
+@pytest.mark.parametrize("chunks", [2, 3, 4, 7])
+def test_pipelined_walk_and_sort(oracle, monkeypatch, chunks):
+    """The chunked walk overlapped with sort + pairwise merges (used for large inputs), forced on small ones."""
+    monkeypatch.setenv("BWTM_PIPELINE_MIN", "1")
+    monkeypatch.setenv("BWTM_PIPELINE_CHUNKS", str(chunks))
+    for shape in ("reads", "noisy_N", "repeats"):
+        ra, bwt_a, rb, bwt_b = collections(oracle, shape)
+        A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+        M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()))
+        assert np.array_equal(M.rle(), oracle.merge(A, B).rle()), (shape, chunks)
+        assert M.timings.walk_kernel_launches == chunks
+    rng = np.random.default_rng(9)
+    g = synth.genome(2000, 42)
+    ra = _variable_reads(rng, g, 200, 1, 300); rb = _variable_reads(rng, g, 150, 1, 300)
+    A, B = oracle.from_comps(oracle.bwt_of_reads(ra)), oracle.from_comps(oracle.bwt_of_reads(rb))
+    assert np.array_equal(FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle())).rle(), oracle.merge(A, B).rle())
