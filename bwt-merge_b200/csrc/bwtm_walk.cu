@@ -373,14 +373,57 @@ template int walk_sequences<uint64_t>(const bwtm_index*, const bwtm_index*, uint
 
 // K2: sort of the RA values (support.h:421 sequentialSort + the merge cascade fmi.cpp:220-257).
 // Only the low `bits` bits are sorted.  The result is in `d_keys` or `d_alt`; returns which.
+//
+// cub's onesweep kernel is latency-bound on B200 (18 % of DRAM bandwidth, 37 % occupancy: profiles/
+// r01_cub_sort_tuning_sweep*.txt); for 4-byte keys a larger tile (384 threads x 24 keys instead of the
+// library's 384 x 19) is the best of the swept configurations (29.8 vs 33.4 ms for 1.51 G keys).
+struct TunedSortHub
+{
+  using KeyT = uint32_t; using ValueT = cub::NullType; using OffsetT = unsigned long long;
+  static constexpr bool KEYS_ONLY = true;
+  using DominantT = KeyT;
+  struct Policy : cub::ChainedPolicy<1000, Policy, Policy>
+  {
+    static constexpr bool ONESWEEP = true;
+    static constexpr int ONESWEEP_RADIX_BITS = 8;
+    static constexpr int PRIMARY_RADIX_BITS = 7, SINGLE_TILE_RADIX_BITS = 6, SEGMENTED_RADIX_BITS = 6;
+    using HistogramPolicy    = cub::AgentRadixSortHistogramPolicy<128, 16, 1, KeyT, ONESWEEP_RADIX_BITS>;
+    using ExclusiveSumPolicy = cub::AgentRadixSortExclusiveSumPolicy<256, ONESWEEP_RADIX_BITS>;
+    using OnesweepPolicy = cub::AgentRadixSortOnesweepPolicy<384, 24, DominantT, 1, cub::RADIX_RANK_MATCH_EARLY_COUNTS_ANY,
+                                                             cub::BLOCK_SCAN_RAKING_MEMOIZE, cub::RADIX_SORT_STORE_DIRECT, ONESWEEP_RADIX_BITS>;
+    // Not launched when ONESWEEP is set, but the dispatch instantiates them.
+    using ScanPolicy = cub::AgentScanPolicy<512, 23, OffsetT, cub::BLOCK_LOAD_WARP_TRANSPOSE, cub::LOAD_DEFAULT, cub::BLOCK_STORE_WARP_TRANSPOSE, cub::BLOCK_SCAN_RAKING_MEMOIZE>;
+    using DownsweepPolicy = cub::AgentRadixSortDownsweepPolicy<512, 23, DominantT, cub::BLOCK_LOAD_TRANSPOSE, cub::LOAD_DEFAULT, cub::RADIX_RANK_MATCH, cub::BLOCK_SCAN_WARP_SCANS, PRIMARY_RADIX_BITS>;
+    using AltDownsweepPolicy = cub::AgentRadixSortDownsweepPolicy<256, 47, DominantT, cub::BLOCK_LOAD_TRANSPOSE, cub::LOAD_DEFAULT, cub::RADIX_RANK_MEMOIZE, cub::BLOCK_SCAN_WARP_SCANS, PRIMARY_RADIX_BITS - 1>;
+    using UpsweepPolicy    = cub::AgentRadixSortUpsweepPolicy<256, 23, DominantT, cub::LOAD_DEFAULT, PRIMARY_RADIX_BITS>;
+    using AltUpsweepPolicy = cub::AgentRadixSortUpsweepPolicy<256, 47, DominantT, cub::LOAD_DEFAULT, PRIMARY_RADIX_BITS - 1>;
+    using SingleTilePolicy = cub::AgentRadixSortDownsweepPolicy<256, 19, DominantT, cub::BLOCK_LOAD_DIRECT, cub::LOAD_LDG, cub::RADIX_RANK_MEMOIZE, cub::BLOCK_SCAN_WARP_SCANS, SINGLE_TILE_RADIX_BITS>;
+    using SegmentedPolicy = cub::AgentRadixSortDownsweepPolicy<192, 39, DominantT, cub::BLOCK_LOAD_TRANSPOSE, cub::LOAD_DEFAULT, cub::RADIX_RANK_MEMOIZE, cub::BLOCK_SCAN_WARP_SCANS, SEGMENTED_RADIX_BITS>;
+    using AltSegmentedPolicy = cub::AgentRadixSortDownsweepPolicy<384, 11, DominantT, cub::BLOCK_LOAD_TRANSPOSE, cub::LOAD_DEFAULT, cub::RADIX_RANK_MEMOIZE, cub::BLOCK_SCAN_WARP_SCANS, SEGMENTED_RADIX_BITS - 1>;
+  };
+  using MaxPolicy = Policy;
+};
+
+static cudaError_t radix_sort_dispatch(void* temp, size_t& bytes, cub::DoubleBuffer<uint32_t>& keys, uint64_t n, int bits, cudaStream_t stream)
+{
+  cub::DoubleBuffer<cub::NullType> values;
+  return cub::DispatchRadixSort<false, uint32_t, cub::NullType, unsigned long long, TunedSortHub>::Dispatch(
+    temp, bytes, keys, values, (unsigned long long)n, 0, bits, true, stream);
+}
+
+static cudaError_t radix_sort_dispatch(void* temp, size_t& bytes, cub::DoubleBuffer<uint64_t>& keys, uint64_t n, int bits, cudaStream_t stream)
+{
+  return cub::DeviceRadixSort::SortKeys(temp, bytes, keys, (int64_t)n, 0, bits, stream);
+}
+
 template<class KeyT>
 int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream)
 {
   cub::DoubleBuffer<KeyT> buffers(d_keys, d_alt);
   size_t temp_bytes = 0;
-  BWTM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, buffers, (int64_t)n, 0, bits, stream));
+  BWTM_CUDA(radix_sort_dispatch(nullptr, temp_bytes, buffers, n, bits, stream));
   DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
-  BWTM_CUDA(cub::DeviceRadixSort::SortKeys(temp.ptr, temp_bytes, buffers, (int64_t)n, 0, bits, stream));
+  BWTM_CUDA(radix_sort_dispatch(temp.ptr, temp_bytes, buffers, n, bits, stream));
   count_launch((uint64_t)(2 + (bits + 7) / 8));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   *sorted = buffers.Current();
