@@ -63,7 +63,7 @@ class Timings(C.Structure):
 
 
 class ReadSegment(C.Structure):
-    _fields_ = [("seed", C.c_uint64), ("reads", C.c_uint64)]
+    _fields_ = [("seed", C.c_uint64), ("reads", C.c_uint64), ("first_read", C.c_uint64)]
 
 
 def build_library(verbose=False):
@@ -206,8 +206,8 @@ class FMI:
 
     @classmethod
     def synthetic(cls, genome_len, genome_seed, read_len, error_threshold, segments):
-        """Fixture: BWT of synthetic reads; segments = [(read_seed, n_reads), ...]."""
-        segs = (ReadSegment * len(segments))(*[ReadSegment(s, n) for s, n in segments])
+        """Fixture: BWT of synthetic reads; segments = [(read_seed, n_reads[, first_read]), ...]."""
+        segs = (ReadSegment * len(segments))(*[ReadSegment(seg[0], seg[1], seg[2] if len(seg) > 2 else 0) for seg in segments])
         h = C.c_void_p()
         check(lib().bwtm_tools_build_synthetic(genome_len, genome_seed, read_len, error_threshold, segs, len(segments), C.byref(h)))
         return cls(h)

@@ -310,30 +310,41 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   // 6. my slice of the merged BWT
   uint64_t a_lo = std::min<uint64_t>(splitter[r], n_a), a_hi = std::min<uint64_t>(splitter[r + 1], n_a);
   uint64_t begin = a_lo + b_lo, end = a_hi + b_lo + recv_total;
-  // A slice that fits one slab has its symbols and runs computed on all ranks at once; only the writer is
-  // chained. Without an explicit slab size the slab is stretched to the slice (up to the 2^31 item limit).
-  uint64_t slab = (options->slab_symbols == 0 && end - begin <= MAX_SLAB_SYMBOLS ? clamp_slab(end - begin, end - begin, true)
-                                                                                : clamp_slab(options->slab_symbols, end - begin));
-  bool single_slab = (end - begin <= slab);
+  // The slice is cut into at most MAX_PARALLEL_SLABS slabs (each below the 2^31 item limit of the run
+  // detection). Symbols, maximal runs and the state-free half of the writer (K4, K3, scan, tile maps) of
+  // every slab are computed on all ranks at once; only SlabEncoder::advance(), which moves the 88-byte writer
+  // state past a slab, is chained through the slabs and ranks; the bytes are written after the state has
+  // been passed on. Slices that would need more slabs (or an explicit small slab size) fall back to running
+  // the whole interleave inside the chain.
+  const uint64_t MAX_PARALLEL_SLABS = 4;
+  uint64_t slice = end - begin;
+  uint64_t slab = (options->slab_symbols == 0 ? clamp_slab(MAX_SLAB_SYMBOLS, slice, true) : clamp_slab(options->slab_symbols, slice));
+  uint64_t n_slabs = div_up(slice, slab);
+  bool parallel = (slice > 0 && n_slabs <= MAX_PARALLEL_SLABS);
 
   DeviceBuffer merged, tile_j, control;
-  SlabEncoder encoder;
+  std::vector<SlabEncoder> encoders(parallel ? n_slabs : 1);
   BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   float interleave_ms = 0.0f, encode_ms = 0.0f;
-  if(single_slab && end > begin)
+  if(parallel)
   {
     BWTM_TRY(merged.allocate(slab));
     BWTM_TRY(tile_j.allocate((slab / interleave_tile_size() + 2) * sizeof(uint64_t)));
-    BWTM_TRY(encoder.init(slab, stream));
-    timer.start();
-    BWTM_TRY(interleave_slab<KeyT>(a, b, slice_keys, b_lo, recv_total, begin, end, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream));
-    interleave_ms += timer.stop();
-    timer.start();
-    BWTM_TRY(encoder.detect(merged.as<uint8_t>(), end - begin, stream));
-    encode_ms += timer.stop();
+    for(uint64_t k = 0; k < n_slabs; k++)
+    {
+      uint64_t p0 = begin + k * slab, p1 = std::min(p0 + slab, end);
+      BWTM_TRY(encoders[k].init(p1 - p0, stream));
+      timer.start();
+      BWTM_TRY(interleave_slab<KeyT>(a, b, slice_keys, b_lo, recv_total, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream));
+      interleave_ms += timer.stop();
+      timer.start();
+      BWTM_TRY(encoders[k].detect(merged.as<uint8_t>(), p1 - p0, stream));
+      encode_ms += timer.stop();
+    }
+    merged.release();
   }
-
   phase.mark("interleave + runs");
+
   // 7. the writer state comes from the previous slice and goes to the next one
   if(r > 0)
   {
@@ -347,9 +358,12 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   uint64_t estimate = (a->rle_bytes + b->rle_bytes) / G;
   int rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream);
   timer.start();
-  if(rc == BWTM_OK && end > begin)
+  if(rc == BWTM_OK && slice > 0)
   {
-    if(single_slab) { rc = encoder.advance(&out, control.as<EncodeControl>(), stream); }
+    if(parallel)
+    {
+      for(uint64_t k = 0; rc == BWTM_OK && k < n_slabs; k++) { rc = encoders[k].advance(&out, control.as<EncodeControl>(), stream); }
+    }
     else
     {
       rc = interleave_range<KeyT>(a, b, slice_keys, b_lo, recv_total, begin, end, options->slab_symbols, &out,
@@ -359,19 +373,23 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   // The next slice only needs the state after this one: it goes out before the bytes are written.
   if(r < G - 1) { BWTM_NCCL(api->Send(control.ptr, sizeof(EncodeControl), ncclUint8, r + 1, comm->comm, stream)); }
-  if(single_slab && end > begin) { rc = encoder.emit(&out, stream); }
+  if(parallel)
+  {
+    for(uint64_t k = 0; rc == BWTM_OK && k < n_slabs; k++) { rc = encoders[k].emit(&out, stream); }
+  }
   if(rc == BWTM_OK && r == G - 1)
   {
-    if(!single_slab || end == begin) { rc = encoder.init(4096, stream); }
-    if(rc == BWTM_OK) { rc = encoder.finish(&out, control.as<EncodeControl>(), stream); }
+    if(!parallel) { rc = encoders[0].init(4096, stream); }
+    if(rc == BWTM_OK) { rc = encoders[0].finish(&out, control.as<EncodeControl>(), stream); }
   }
   if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
-  if(single_slab) { encode_ms += timer.stop(); } else { timer.stop(); }
+  if(parallel) { encode_ms += timer.stop(); } else { timer.stop(); }
   BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   timings->interleave_seconds = interleave_ms * 1e-3;
   timings->encode_seconds = encode_ms * 1e-3;
-  received.release(); received_alt.release(); merged.release();
+  received.release(); received_alt.release();
+  encoders.clear();
 
   phase.mark("chained writer");
   // 8. every rank gets the complete run-length BWT

@@ -43,16 +43,17 @@ __global__ void gen_genome(uint8_t* __restrict__ genome, uint64_t length, uint64
 
 // One thread per base of the segment's reads.
 __global__ void gen_reads(const uint8_t* __restrict__ genome, uint64_t genome_len, uint64_t reads, uint64_t read_len,
-                          uint64_t threshold, uint64_t base_start, uint64_t base_sub, uint64_t base_shift,
+                          uint64_t first_read, uint64_t threshold, uint64_t base_start, uint64_t base_sub, uint64_t base_shift,
                           uint8_t* __restrict__ out)
 {
-  uint64_t cell = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(cell >= reads * read_len) { return; }
-  uint64_t read = cell / read_len, k = cell - read * read_len;
+  uint64_t local = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(local >= reads * read_len) { return; }
+  uint64_t read = first_read + local / read_len, k = local % read_len;
+  uint64_t cell = read * read_len + k;
   uint64_t start = mix64(base_start + read) % (genome_len - read_len + 1);
   uint32_t b = genome[start + k] - 1u;
   if((mix64(base_sub + cell) >> 11) < threshold) { b = (b + 1u + (uint32_t)(mix64(base_shift + cell) % 3u)) & 3u; }
-  out[cell] = (uint8_t)(b + 1u);
+  out[local] = (uint8_t)(b + 1u);
 }
 
 //------------------------------------------------------------------------------
@@ -227,7 +228,7 @@ int bwtm_tools_build_synthetic(uint64_t genome_len, uint64_t genome_seed, uint64
   {
     uint64_t cells = segments[s].reads * read_len;
     if(cells == 0) { continue; }
-    gen_reads<<<(unsigned)div_up(cells, 256), 256>>>(genome.as<uint8_t>(), genome_len, segments[s].reads, read_len, error_threshold,
+    gen_reads<<<(unsigned)div_up(cells, 256), 256>>>(genome.as<uint8_t>(), genome_len, segments[s].reads, read_len, segments[s].first_read, error_threshold,
                                                      stream_base(segments[s].seed, 1), stream_base(segments[s].seed, 2),
                                                      stream_base(segments[s].seed, 3), matrix.as<uint8_t>() + first * read_len);
     BWTM_LAUNCH_CHECK();

@@ -196,6 +196,7 @@ typedef struct
 {
   uint64_t seed;        /* read seed */
   uint64_t reads;       /* number of reads in this segment */
+  uint64_t first_read;  /* index of the segment's first read within the seed's read stream */
 } bwtm_read_segment;
 
 int bwtm_tools_build_synthetic(uint64_t genome_len, uint64_t genome_seed, uint64_t read_len,

@@ -19,7 +19,7 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
     thr = synth.error_threshold(0.01)
-    cases = [(200000, 20000, 100, 0), (50000, 3000, 60, 8192), (3000, 5, 40, 4096), (100, 1, 30, 0)]
+    cases = [(200000, 20000, 100, 0), (200000, 20000, 100, 524288), (200000, 16000, 100, 262144), (50000, 3000, 60, 8192), (3000, 5, 40, 4096), (100, 1, 30, 0)]
     for G, n, L, slab in cases:
         A = FMI.synthetic(G, 42, L, thr, [(1, n)]); B = FMI.synthetic(G, 42, L, thr, [(2, max(1, n // 2))])
         p = MergeParameters(); p.slab_symbols = slab
