@@ -392,30 +392,75 @@ int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cu
   return BWTM_OK;
 }
 
+// Number of maximal runs of a symbol array (positions whose symbol differs from the previous one).
+__global__ void __launch_bounds__(256)
+count_runs(const uint8_t* __restrict__ symbols, uint64_t n, unsigned long long* __restrict__ result)
+{
+  __shared__ unsigned int block_total;
+  if(threadIdx.x == 0) { block_total = 0; }
+  __syncthreads();
+  unsigned int local = 0;
+  const uint64_t vectors = n / 16;
+  const uint4* v = reinterpret_cast<const uint4*>(symbols);
+  for(uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < vectors; k += (uint64_t)gridDim.x * blockDim.x)
+  {
+    uint4 q = v[k];
+    uint32_t w[4] = { q.x, q.y, q.z, q.w };
+    uint32_t previous = (k == 0 ? 0xFFFFFFFFu : (uint32_t)symbols[16 * k - 1]);
+#pragma unroll
+    for(int j = 0; j < 4; j++)
+    {
+      uint32_t shifted = (w[j] << 8) | (j == 0 ? (previous & 0xFFu) : (w[j - 1] >> 24));
+      uint32_t diff = w[j] ^ shifted;                         // byte i != byte i - 1  <=>  byte i of diff != 0
+      uint32_t nonzero = ((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff;
+      local += __popc(nonzero & 0x80808080u);
+    }
+    if(k == 0) { local += ((w[0] & 0xFFu) == 0xFFu ? 1u : 0u); }   // the first symbol always starts a run (0xFF never occurs)
+  }
+  if(blockIdx.x == 0 && threadIdx.x == 0)
+  {
+    for(uint64_t i = vectors * 16; i < n; i++) { local += (i == 0 || symbols[i] != symbols[i - 1]) ? 1u : 0u; }
+  }
+#pragma unroll
+  for(int offset = 16; offset > 0; offset >>= 1) { local += __shfl_down_sync(0xFFFFFFFFu, local, offset); }
+  if((threadIdx.x & 31) == 0 && local != 0) { atomicAdd(&block_total, local); }
+  __syncthreads();
+  if(threadIdx.x == 0 && block_total != 0) { atomicAdd(result, (unsigned long long)block_total); }
+}
+
 int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
 {
   max_symbols = max_symbols_;
-  uint64_t max_long = max_symbols / MAX_RUN + 1;
-  uint64_t max_long_tiles = div_up(max_long, LONG_TILE);
-  BWTM_TRY(run_sym.allocate(max_symbols));
-  BWTM_TRY(run_len.allocate(max_symbols * sizeof(uint32_t)));
+  run_capacity = 0;
   BWTM_TRY(num_runs.allocate(4 * sizeof(uint64_t)));
   BWTM_TRY(placed.allocate(sizeof(EncodeControl)));
-  BWTM_TRY(scan.allocate(max_symbols * sizeof(unsigned long long)));
+  size_t rle_temp = 0, scan_temp = 0;
+  BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_temp, (const uint8_t*)nullptr, (uint8_t*)nullptr,
+                                                (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_symbols, stream));
+  {
+    cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes((const uint32_t*)nullptr, RunClass());
+    BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, classes, (unsigned long long*)nullptr, (int64_t)max_symbols, stream));
+  }
+  BWTM_TRY(cub_temp.allocate(std::max(rle_temp, scan_temp)));
+  return BWTM_OK;
+}
+
+// Work arrays sized by the number of runs of the slab (a fifth of the symbols for read collections), grow-only.
+int SlabEncoder::reserve_runs(uint64_t runs)
+{
+  if(runs <= run_capacity) { return BWTM_OK; }
+  uint64_t capacity = runs + (runs >> 3) + 1024;
+  uint64_t max_long = std::min(capacity, max_symbols / MAX_RUN + 1);
+  uint64_t max_long_tiles = div_up(max_long, LONG_TILE);
+  BWTM_TRY(run_sym.allocate(capacity));
+  BWTM_TRY(run_len.allocate(capacity * sizeof(uint32_t)));
+  BWTM_TRY(scan.allocate(capacity * sizeof(unsigned long long)));
   BWTM_TRY(long_list.allocate(max_long * sizeof(uint32_t)));
   BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
   BWTM_TRY(tile_bytes.allocate(max_long_tiles * 64 * sizeof(uint32_t)));
   BWTM_TRY(tile_entry.allocate(max_long_tiles * sizeof(unsigned long long)));
   BWTM_TRY(checkpoints.allocate((max_long / LONG_SUB + 1) * 64 * sizeof(uint16_t)));
-
-  size_t rle_temp = 0, scan_temp = 0;
-  BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_temp, (const uint8_t*)nullptr, run_sym.as<uint8_t>(),
-                                                run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)max_symbols, stream));
-  {
-    cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes(run_len.as<uint32_t>(), RunClass());
-    BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, classes, scan.as<unsigned long long>(), (int64_t)max_symbols, stream));
-  }
-  BWTM_TRY(cub_temp.allocate(std::max(rle_temp, scan_temp)));
+  run_capacity = capacity;
   return BWTM_OK;
 }
 
@@ -428,13 +473,27 @@ int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t
   if(symbols > max_symbols) { set_error("slab of %llu symbols exceeds the encoder capacity", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
   size_t temp_bytes = cub_temp.bytes;
   BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, 4 * sizeof(uint64_t), stream));
+  {
+    unsigned long long* counter = num_runs.as<unsigned long long>() + 3;
+    count_runs<<<(unsigned)std::min<uint64_t>(div_up(symbols, 256 * 16), 148 * 16), 256, 0, stream>>>(d_symbols, symbols, counter);
+    BWTM_LAUNCH_CHECK();
+    unsigned long long expected = 0;
+    BWTM_CUDA(cudaMemcpyAsync(&expected, counter, sizeof(expected), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    BWTM_TRY(this->reserve_runs(expected));
+  }
   BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(cub_temp.ptr, temp_bytes, d_symbols, run_sym.as<uint8_t>(),
                                                 run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)symbols, stream));
   count_launch(3);
   uint64_t m = 0;
   BWTM_CUDA(cudaMemcpyAsync(&m, num_runs.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  if(m == 0) { set_error("run-length encode produced no runs for %llu symbols", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
+  if(m == 0 || m > run_capacity)
+  {
+    set_error("run detection found %llu runs in %llu symbols (capacity %llu)", (unsigned long long)m, (unsigned long long)symbols,
+              (unsigned long long)run_capacity);
+    return BWTM_ERR_INTERNAL;
+  }
   detected_runs = m;
   if(m < 3) { return BWTM_OK; }
 

@@ -180,21 +180,26 @@ gather_kernel(const uint4* __restrict__ table, uint64_t granules, uint64_t loads
   if(acc == 0x12345678u) { sink[0] = acc; }
 }
 
-template<int GRANULE>
+// Dependent random record reads in the shape of the rank/LF kernel: LANES lanes share one walker and read
+// one GRANULE-byte record with a single instruction (lane j reads 16-byte piece j, or pieces 2j and 2j+1).
+template<int GRANULE, int LANES>
 __global__ void __launch_bounds__(256)
 chase_kernel(const uint4* __restrict__ table, uint64_t granules, uint64_t steps, uint64_t seed, uint32_t* __restrict__ sink)
 {
   uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  uint64_t state = mix64(seed + tid);
+  uint64_t walker = tid / LANES; int sub = (int)(tid % LANES);
+  constexpr int VEC = GRANULE / 16, PER_LANE = VEC / LANES;
+  uint64_t state = mix64(seed + walker);
   uint32_t acc = 0;
-  constexpr int VEC = GRANULE / 16;
   for(uint64_t k = 0; k < steps; k++)
   {
     uint64_t g = __umul64hi(state, granules);
-    const uint4* p = table + g * VEC;
+    const uint4* p = table + g * VEC + sub * PER_LANE;
     uint32_t x = 0;
 #pragma unroll
-    for(int v = 0; v < VEC; v++) { uint4 q = __ldg(p + v); x ^= q.x ^ q.y ^ q.z ^ q.w; }
+    for(int v = 0; v < PER_LANE; v++) { uint4 q = __ldg(p + v); x ^= q.x ^ q.y ^ q.z ^ q.w; }
+#pragma unroll
+    for(int o = 1; o < LANES; o <<= 1) { x ^= __shfl_xor_sync(0xFFFFFFFFu, x, o); }
     acc ^= x;
     state = state * 6364136223846793005ull + 1442695040888963407ull + x;   // the next address depends on the data
   }
@@ -306,7 +311,9 @@ int bwtm_tools_chase_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_lo
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   uint64_t threads = (uint64_t)sms * threads_per_sm;
-  uint64_t steps = std::max<uint64_t>(1, n_loads / threads);
+  const uint64_t lanes = (granule == 32 ? 2 : 4);
+  uint64_t walkers = threads / lanes;
+  uint64_t steps = std::max<uint64_t>(1, n_loads / walkers);
   uint64_t granules = table_bytes / granule;
   unsigned grid = (unsigned)(threads / 256);
   cudaEvent_t begin, end;
@@ -315,14 +322,14 @@ int bwtm_tools_chase_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_lo
   for(int it = 0; it < 3; it++)
   {
     BWTM_CUDA(cudaEventRecord(begin));
-    if(granule == 32)       { chase_kernel<32><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
-    else if(granule == 64)  { chase_kernel<64><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
-    else                    { chase_kernel<128><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
+    if(granule == 32)       { chase_kernel<32, 2><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
+    else if(granule == 64)  { chase_kernel<64, 4><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
+    else                    { chase_kernel<128, 4><<<grid, 256>>>(table.as<uint4>(), granules, steps, 99 + it, sink.as<uint32_t>()); }
     BWTM_LAUNCH_CHECK();
     BWTM_CUDA(cudaEventRecord(end));
     BWTM_CUDA(cudaEventSynchronize(end));
     float ms = 0.0f; BWTM_CUDA(cudaEventElapsedTime(&ms, begin, end));
-    double gbs = (double)(threads * steps) * granule / (ms * 1e-3) / 1e9;
+    double gbs = (double)(walkers * steps) * granule / (ms * 1e-3) / 1e9;
     if(it > 0 && gbs > best) { best = gbs; }
   }
   cudaEventDestroy(begin); cudaEventDestroy(end);

@@ -211,9 +211,10 @@ int bwtm_tools_build_from_reads(const uint8_t* read_comps, uint64_t reads, uint6
 int bwtm_tools_gather_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_loads, int iterations,
                             double* gbytes_per_second);
 
-/* The same with the access pattern of the rank/LF kernel: every thread follows a chain of DEPENDENT
-   loads (the next address depends on the loaded data), `threads_per_sm` resident threads per SM (multiple
-   of 256, at most 2048). If l2_fetch_granularity is 32, 64 or 128, cudaLimitMaxL2FetchGranularity is set to
+/* The same with the access pattern of the rank/LF kernel: walkers follow chains of DEPENDENT record reads
+   (the next address depends on the loaded data); 4 lanes share a walker and read its record with one
+   instruction (2 lanes for 32-byte records); `threads_per_sm` resident threads per SM (multiple of 256, at
+   most 2048). The result divided by `granule` is the random record (= line request) rate. If l2_fetch_granularity is 32, 64 or 128, cudaLimitMaxL2FetchGranularity is set to
    it first (0 = leave unchanged). */
 int bwtm_tools_chase_bench(uint64_t table_bytes, uint32_t granule, uint64_t n_loads, uint32_t threads_per_sm,
                            uint32_t l2_fetch_granularity, double* gbytes_per_second);
