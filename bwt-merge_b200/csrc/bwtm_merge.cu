@@ -185,7 +185,7 @@ __device__ __forceinline__ uint32_t write_run(uint8_t* __restrict__ out, uint64_
 // absorbs the slab's first run when the symbols agree; it is written as soon as the slab shows that it
 // has ended; the slab's last run becomes the new pending run. The runs in between, [1, m - 1), never
 // depend on the pending run: they are the parallel part.
-__global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ len,
+__global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ start,
                          uint64_t m, uint8_t* __restrict__ out, int finish)
 {
   if(blockIdx.x != 0 || threadIdx.x != 0) { return; }
@@ -202,7 +202,7 @@ __global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, co
   }
   if(m > 0)
   {
-    if(ctl->carry_len > 0 && sym[0] == ctl->carry_sym) { ctl->carry_len += len[0]; }
+    if(ctl->carry_len > 0 && sym[0] == ctl->carry_sym) { ctl->carry_len += start[1] - start[0]; }
     else
     {
       if(ctl->carry_len > 0)
@@ -210,33 +210,36 @@ __global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, co
         ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
         ctl->runs_total++;
       }
-      ctl->carry_sym = sym[0]; ctl->carry_len = len[0];
+      ctl->carry_sym = sym[0]; ctl->carry_len = start[1] - start[0];
     }
     if(m > 1)
     {
       ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
       ctl->runs_total++;
-      ctl->carry_sym = sym[m - 1]; ctl->carry_len = len[m - 1];
+      ctl->carry_sym = sym[m - 1]; ctl->carry_len = start[m] - start[m - 1];
       ctl->count = m - 2;
     }
   }
   ctl->slab_base = ctl->out_size;
 }
 
+// Runs are stored as (symbol, start position in the slab); start[m] = slab length closes the last run.
 struct RunClass   // 1 in the low word for a short run, 1 in the high word for a long run
 {
-  __host__ __device__ __forceinline__ unsigned long long operator()(const uint32_t& length) const
+  const uint32_t* start;
+  __host__ __device__ __forceinline__ unsigned long long operator()(const uint64_t& k) const
   {
-    return (length < (uint32_t)MAX_RUN ? 1ull : (1ull << 32));
+    return (start[k + 1] - start[k] < (uint32_t)MAX_RUN ? 1ull : (1ull << 32));
   }
 };
+using RunClassIterator = cub::TransformInputIterator<unsigned long long, RunClass, cub::CountingInputIterator<uint64_t>>;
 
-__global__ void enc_collect_long(unsigned long long* __restrict__ stats, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+__global__ void enc_collect_long(unsigned long long* __restrict__ stats, const uint32_t* __restrict__ start, const unsigned long long* __restrict__ scan,
                                  uint64_t count, uint32_t* __restrict__ long_list)
 {
   uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(k >= count) { return; }
-  uint32_t length = len[k];
+  uint32_t length = start[k + 1] - start[k];
   unsigned long long s = scan[k];
   bool is_long = (length >= (uint32_t)MAX_RUN);
   if(is_long) { long_list[s >> 32] = (uint32_t)k; }
@@ -264,7 +267,7 @@ __device__ __forceinline__ uint32_t natural_bytes(uint32_t length)   // length >
 // runs. A long run preceded by `before` short runs starts at offset residue (before + q) mod 64, so the maps
 // do not depend on where the slab lands in the output: they are computed before the writer state is known.
 __global__ void __launch_bounds__(64)
-enc_tile_maps(const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+enc_tile_maps(const uint32_t* __restrict__ start, const unsigned long long* __restrict__ scan,
               const uint32_t* __restrict__ long_list, uint64_t n_long, uint32_t* __restrict__ tile_bytes,
               uint16_t* __restrict__ checkpoints)
 {
@@ -280,7 +283,7 @@ enc_tile_maps(const uint32_t* __restrict__ len, const unsigned long long* __rest
     if(threadIdx.x < LONG_SUB && chunk + threadIdx.x < last)
     {
       uint32_t idx = long_list[chunk + threadIdx.x];
-      uint32_t length = len[idx];
+      uint32_t length = start[idx + 1] - start[idx];
       s_len[threadIdx.x] = length; s_nat[threadIdx.x] = natural_bytes(length);
       s_before[threadIdx.x] = (uint32_t)scan[idx];
     }
@@ -333,7 +336,7 @@ enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint6
 
 // One thread per sub-tile of LONG_SUB long runs: starts from the tile's true entry and the checkpoint of
 // that entry residue.
-__global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __restrict__ len, const unsigned long long* __restrict__ scan,
+__global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __restrict__ start, const unsigned long long* __restrict__ scan,
                                  const uint32_t* __restrict__ long_list, uint64_t n_long,
                                  const unsigned long long* __restrict__ tile_entry, const uint16_t* __restrict__ checkpoints,
                                  uint32_t* __restrict__ long_offset)
@@ -348,14 +351,14 @@ __global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __res
   for(uint64_t k = first; k < last; k++)
   {
     uint32_t idx = long_list[k];
-    uint32_t length = len[idx];
+    uint32_t length = start[idx + 1] - start[idx];
     long_offset[k] = (uint32_t)p;
     uint32_t state = (base_state + (uint32_t)scan[idx] + (uint32_t)p) & 63u;
     p += long_run_bytes_fast(length, natural_bytes(length), state);
   }
 }
 
-__global__ void enc_write(const EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ len,
+__global__ void enc_write(const EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ start,
                           const unsigned long long* __restrict__ scan, const uint32_t* __restrict__ long_offset,
                           uint64_t count, uint8_t* __restrict__ out)
 {
@@ -365,7 +368,7 @@ __global__ void enc_write(const EncodeControl* ctl, const uint8_t* __restrict__ 
   uint64_t longs_before = s >> 32;
   uint64_t bytes_before = (s & 0xFFFFFFFFull) + (longs_before < ctl->n_long ? (uint64_t)long_offset[longs_before] : ctl->long_bytes);
   uint64_t offset = ctl->slab_base + bytes_before;
-  uint32_t length = len[k], comp = sym[k];
+  uint32_t length = start[k + 1] - start[k], comp = sym[k];
   if(length < (uint32_t)MAX_RUN) { out[offset] = (uint8_t)(comp + SIGMA * (length - 1)); }
   else { write_run(out, offset, comp, length); }
 }
@@ -392,40 +395,98 @@ int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cu
   return BWTM_OK;
 }
 
-// Number of maximal runs of a symbol array (positions whose symbol differs from the previous one).
-__global__ void __launch_bounds__(256)
-count_runs(const uint8_t* __restrict__ symbols, uint64_t n, unsigned long long* __restrict__ result)
+// K3: maximal runs of a symbol array (what the reference's RunBuffer produces, utils.h:121-142).
+// A run starts wherever a symbol differs from its predecessor. Pass 1 counts the run starts of every
+// RUN_TILE-symbol tile, a scan turns the counts into offsets, pass 2 writes (symbol, start) for every run.
+constexpr int RUN_THREADS = 256;
+constexpr int RUN_TILE    = RUN_THREADS * 16;
+
+// Bit i of the result is set when symbol i of the 16 differs from the one before it (`previous` for i = 0).
+__device__ __forceinline__ uint32_t run_start_flags(const uint4& q, uint32_t previous)
 {
-  __shared__ unsigned int block_total;
-  if(threadIdx.x == 0) { block_total = 0; }
-  __syncthreads();
-  unsigned int local = 0;
-  const uint64_t vectors = n / 16;
-  const uint4* v = reinterpret_cast<const uint4*>(symbols);
-  for(uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < vectors; k += (uint64_t)gridDim.x * blockDim.x)
-  {
-    uint4 q = v[k];
-    uint32_t w[4] = { q.x, q.y, q.z, q.w };
-    uint32_t previous = (k == 0 ? 0xFFFFFFFFu : (uint32_t)symbols[16 * k - 1]);
+  uint32_t w[4] = { q.x, q.y, q.z, q.w };
+  uint32_t flags = 0;
 #pragma unroll
-    for(int j = 0; j < 4; j++)
-    {
-      uint32_t shifted = (w[j] << 8) | (j == 0 ? (previous & 0xFFu) : (w[j - 1] >> 24));
-      uint32_t diff = w[j] ^ shifted;                         // byte i != byte i - 1  <=>  byte i of diff != 0
-      uint32_t nonzero = ((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff;
-      local += __popc(nonzero & 0x80808080u);
-    }
-    if(k == 0) { local += ((w[0] & 0xFFu) == 0xFFu ? 1u : 0u); }   // the first symbol always starts a run (0xFF never occurs)
-  }
-  if(blockIdx.x == 0 && threadIdx.x == 0)
+  for(int j = 0; j < 4; j++)
   {
-    for(uint64_t i = vectors * 16; i < n; i++) { local += (i == 0 || symbols[i] != symbols[i - 1]) ? 1u : 0u; }
+    uint32_t shifted = (w[j] << 8) | (j == 0 ? (previous & 0xFFu) : (w[j - 1] >> 24));
+    uint32_t diff = w[j] ^ shifted;
+    uint32_t nonzero = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;   // high bit of every differing byte
+    // gather the four high bits into a nibble
+    uint32_t nibble = ((nonzero >> 7) & 1u) | ((nonzero >> 14) & 2u) | ((nonzero >> 21) & 4u) | ((nonzero >> 28) & 8u);
+    flags |= nibble << (4 * j);
   }
+  return flags;
+}
+
+// Loads the 16 symbols of slot `slot` (zero-padded beyond n) and the symbol before them (0xFF at the start).
+__device__ __forceinline__ uint4 load_symbols16(const uint8_t* __restrict__ symbols, uint64_t n, uint64_t slot, uint32_t& previous, int& valid)
+{
+  uint64_t first = slot * 16;
+  valid = (first >= n ? 0 : (n - first < 16 ? (int)(n - first) : 16));
+  previous = (first == 0 || first > n ? 0xFFu : (uint32_t)symbols[first - 1]);
+  uint4 q = make_uint4(0, 0, 0, 0);
+  if(valid == 16) { q = *reinterpret_cast<const uint4*>(symbols + first); }
+  else if(valid > 0)
+  {
+    uint32_t w[4] = { 0, 0, 0, 0 };
+    for(int i = 0; i < valid; i++) { w[i >> 2] |= (uint32_t)symbols[first + i] << (8 * (i & 3)); }
+    q = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  return q;
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+run_tile_counts(const uint8_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ tile_counts)
+{
+  __shared__ uint32_t warp_sums[RUN_THREADS / 32];
+  uint32_t previous; int valid;
+  uint4 q = load_symbols16(symbols, n, (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x, previous, valid);
+  uint32_t flags = run_start_flags(q, previous) & ((1u << valid) - 1u);
+  uint32_t count = __popc(flags);
 #pragma unroll
-  for(int offset = 16; offset > 0; offset >>= 1) { local += __shfl_down_sync(0xFFFFFFFFu, local, offset); }
-  if((threadIdx.x & 31) == 0 && local != 0) { atomicAdd(&block_total, local); }
+  for(int offset = 16; offset > 0; offset >>= 1) { count += __shfl_down_sync(0xFFFFFFFFu, count, offset); }
+  if((threadIdx.x & 31) == 0) { warp_sums[threadIdx.x >> 5] = count; }
   __syncthreads();
-  if(threadIdx.x == 0 && block_total != 0) { atomicAdd(result, (unsigned long long)block_total); }
+  if(threadIdx.x == 0)
+  {
+    uint32_t total = 0;
+    for(int w = 0; w < RUN_THREADS / 32; w++) { total += warp_sums[w]; }
+    tile_counts[blockIdx.x] = total;
+  }
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+run_tile_write(const uint8_t* __restrict__ symbols, uint64_t n, const uint32_t* __restrict__ tile_offsets,
+               uint8_t* __restrict__ run_sym, uint32_t* __restrict__ run_start)
+{
+  __shared__ uint32_t warp_sums[RUN_THREADS / 32];
+  uint32_t previous; int valid;
+  uint64_t slot = (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x;
+  uint4 q = load_symbols16(symbols, n, slot, previous, valid);
+  uint32_t flags = run_start_flags(q, previous) & ((1u << valid) - 1u);
+  uint32_t count = __popc(flags);
+  // exclusive prefix of the counts within the block
+  uint32_t inclusive = count;
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for(int offset = 1; offset < 32; offset <<= 1)
+  {
+    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane >= offset) { inclusive += v; }
+  }
+  if(lane == 31) { warp_sums[threadIdx.x >> 5] = inclusive; }
+  __syncthreads();
+  uint32_t before = tile_offsets[blockIdx.x] + inclusive - count;
+  for(int w = 0; w < (int)(threadIdx.x >> 5); w++) { before += warp_sums[w]; }
+  uint32_t words[4] = { q.x, q.y, q.z, q.w };
+  while(flags != 0)
+  {
+    int i = __ffs(flags) - 1; flags &= flags - 1;
+    run_sym[before] = (uint8_t)(words[i >> 2] >> (8 * (i & 3)));
+    run_start[before] = (uint32_t)(slot * 16 + i);
+    before++;
+  }
 }
 
 int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
@@ -434,14 +495,15 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   run_capacity = 0;
   BWTM_TRY(num_runs.allocate(4 * sizeof(uint64_t)));
   BWTM_TRY(placed.allocate(sizeof(EncodeControl)));
-  size_t rle_temp = 0, scan_temp = 0;
-  BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(nullptr, rle_temp, (const uint8_t*)nullptr, (uint8_t*)nullptr,
-                                                (uint32_t*)nullptr, (uint32_t*)nullptr, (int)max_symbols, stream));
+  uint64_t tiles = div_up(max_symbols, RUN_TILE) + 1;
+  BWTM_TRY(run_tiles.allocate(tiles * sizeof(uint32_t)));
+  size_t tile_temp = 0, scan_temp = 0;
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tile_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)tiles, stream));
   {
-    cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes((const uint32_t*)nullptr, RunClass());
+    RunClassIterator classes(cub::CountingInputIterator<uint64_t>(0), RunClass{ nullptr });
     BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, classes, (unsigned long long*)nullptr, (int64_t)max_symbols, stream));
   }
-  BWTM_TRY(cub_temp.allocate(std::max(rle_temp, scan_temp)));
+  BWTM_TRY(cub_temp.allocate(std::max(tile_temp, scan_temp)));
   return BWTM_OK;
 }
 
@@ -453,7 +515,7 @@ int SlabEncoder::reserve_runs(uint64_t runs)
   uint64_t max_long = std::min(capacity, max_symbols / MAX_RUN + 1);
   uint64_t max_long_tiles = div_up(max_long, LONG_TILE);
   BWTM_TRY(run_sym.allocate(capacity));
-  BWTM_TRY(run_len.allocate(capacity * sizeof(uint32_t)));
+  BWTM_TRY(run_start.allocate((capacity + 1) * sizeof(uint32_t)));
   BWTM_TRY(scan.allocate(capacity * sizeof(unsigned long long)));
   BWTM_TRY(long_list.allocate(max_long * sizeof(uint32_t)));
   BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
@@ -473,34 +535,30 @@ int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t
   if(symbols > max_symbols) { set_error("slab of %llu symbols exceeds the encoder capacity", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
   size_t temp_bytes = cub_temp.bytes;
   BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, 4 * sizeof(uint64_t), stream));
-  {
-    unsigned long long* counter = num_runs.as<unsigned long long>() + 3;
-    count_runs<<<(unsigned)std::min<uint64_t>(div_up(symbols, 256 * 16), 148 * 16), 256, 0, stream>>>(d_symbols, symbols, counter);
-    BWTM_LAUNCH_CHECK();
-    unsigned long long expected = 0;
-    BWTM_CUDA(cudaMemcpyAsync(&expected, counter, sizeof(expected), cudaMemcpyDeviceToHost, stream));
-    BWTM_CUDA(cudaStreamSynchronize(stream));
-    BWTM_TRY(this->reserve_runs(expected));
-  }
-  BWTM_CUDA(cub::DeviceRunLengthEncode::Encode(cub_temp.ptr, temp_bytes, d_symbols, run_sym.as<uint8_t>(),
-                                                run_len.as<uint32_t>(), num_runs.as<uint32_t>(), (int)symbols, stream));
-  count_launch(3);
-  uint64_t m = 0;
-  BWTM_CUDA(cudaMemcpyAsync(&m, num_runs.ptr, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  uint64_t tiles = div_up(symbols, RUN_TILE);
+  run_tile_counts<<<(unsigned)tiles, RUN_THREADS, 0, stream>>>(d_symbols, symbols, run_tiles.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemsetAsync(run_tiles.as<uint32_t>() + tiles, 0, sizeof(uint32_t), stream));
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, run_tiles.as<uint32_t>(), run_tiles.as<uint32_t>(), (int64_t)(tiles + 1), stream));
+  count_launch(2);
+  uint32_t total_runs = 0;
+  BWTM_CUDA(cudaMemcpyAsync(&total_runs, run_tiles.as<uint32_t>() + tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  if(m == 0 || m > run_capacity)
-  {
-    set_error("run detection found %llu runs in %llu symbols (capacity %llu)", (unsigned long long)m, (unsigned long long)symbols,
-              (unsigned long long)run_capacity);
-    return BWTM_ERR_INTERNAL;
-  }
+  uint64_t m = total_runs;
+  if(m == 0) { set_error("run detection found no runs in %llu symbols", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
+  BWTM_TRY(this->reserve_runs(m));
+  run_tile_write<<<(unsigned)tiles, RUN_THREADS, 0, stream>>>(d_symbols, symbols, run_tiles.as<uint32_t>(), run_sym.as<uint8_t>(), run_start.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  uint32_t slab_length = (uint32_t)symbols;
+  BWTM_CUDA(cudaMemcpyAsync(run_start.as<uint32_t>() + m, &slab_length, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
   detected_runs = m;
   if(m < 3) { return BWTM_OK; }
 
   uint64_t count = m - 2;
-  const uint32_t* len = run_len.as<uint32_t>() + 1;
+  const uint32_t* len = run_start.as<uint32_t>() + 1;   // starts of the parallel part, runs [1, m - 1)
   unsigned long long* stats = num_runs.as<unsigned long long>() + 1;
-  cub::TransformInputIterator<unsigned long long, RunClass, const uint32_t*> classes(len, RunClass());
+  RunClassIterator classes(cub::CountingInputIterator<uint64_t>(0), RunClass{ len });
   BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, classes, scan.as<unsigned long long>(), (int64_t)count, stream));
   count_launch(2);
   enc_collect_long<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(stats, len, scan.as<unsigned long long>(), count, long_list.as<uint32_t>());
@@ -531,7 +589,7 @@ int SlabEncoder::advance(OutputBuffer* out, EncodeControl* d_control, cudaStream
   BWTM_CUDA(cudaStreamSynchronize(stream));
   // Upper bound of what this slab can add: two sequential runs, one byte per short run, 16 per long run.
   BWTM_TRY(ensure_capacity(out, ctl.out_size + 512 + part_short + 16 * part_long, ctl.out_size, stream));
-  enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_len.as<uint32_t>(), m, out->at_origin(), 0);
+  enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_start.as<uint32_t>(), m, out->at_origin(), 0);
   BWTM_LAUNCH_CHECK();
   if(part_count == 0) { return BWTM_OK; }
   uint64_t long_tiles = div_up(part_long, LONG_TILE);
@@ -547,7 +605,7 @@ int SlabEncoder::emit(OutputBuffer* out, cudaStream_t stream)
   if(detected_runs == 0 || part_count == 0) { return BWTM_OK; }
   const EncodeControl* where = placed.as<EncodeControl>();
   const uint8_t* sym = run_sym.as<uint8_t>() + 1;
-  const uint32_t* len = run_len.as<uint32_t>() + 1;
+  const uint32_t* len = run_start.as<uint32_t>() + 1;
   if(part_long > 0)
   {
     enc_long_offsets<<<(unsigned)div_up(div_up(part_long, LONG_SUB), 128), 128, 0, stream>>>(

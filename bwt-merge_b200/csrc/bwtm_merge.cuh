@@ -76,7 +76,7 @@ struct SlabEncoder
 {
   uint64_t max_symbols;
   uint64_t run_capacity;                        // runs the work arrays can hold
-  DeviceBuffer run_sym, run_len, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, placed, cub_temp;
+  DeviceBuffer run_sym, run_start, run_tiles, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, placed, cub_temp;
   uint64_t detected_runs;                       // result of detect(): maximal runs of the slab
   uint64_t part_count, part_short, part_long;   // its parallel part, runs [1, m - 1)
   int init(uint64_t max_symbols, cudaStream_t stream);
