@@ -28,7 +28,7 @@ namespace bwtm
 constexpr int TILE        = 4096;
 constexpr int IL_THREADS  = 256;
 constexpr int PER_THREAD  = TILE / IL_THREADS;   // 16
-constexpr int LONG_TILE   = 1024;                // long runs per transducer tile
+constexpr int LONG_TILE   = 2048;                // long runs per transducer tile (at most 16 bytes each: checkpoints fit 16 bits)
 constexpr int LONG_SUB    = 32;                  // long runs per checkpointed sub-tile
 constexpr int SCAN_CHUNK  = 128;                 // tile maps staged in shared memory per step of the tile scan
 
@@ -64,10 +64,13 @@ __device__ __forceinline__ uint32_t fetch_symbol(const DeviceIndex& idx, uint64_
 template<class KeyT>
 __global__ void __launch_bounds__(IL_THREADS)
 k4_interleave(DeviceIndex a, DeviceIndex b, const KeyT* __restrict__ keys, uint64_t key_base,
-              const uint64_t* __restrict__ tile_j, uint64_t begin, uint64_t end, uint8_t* __restrict__ merged)
+              const uint64_t* __restrict__ tile_j, uint64_t begin, uint64_t end, uint8_t* __restrict__ merged,
+              unsigned long long* __restrict__ distinct_keys)
 {
   __shared__ uint32_t bitmap[TILE / 32];
   __shared__ uint32_t prefix[TILE / 32];
+  __shared__ uint32_t distinct;
+  if(threadIdx.x == 0) { distinct = 0; }
 
   const int tid = threadIdx.x;
   uint64_t d0 = begin + (uint64_t)blockIdx.x * TILE;
@@ -77,13 +80,18 @@ k4_interleave(DeviceIndex a, DeviceIndex b, const KeyT* __restrict__ keys, uint6
 
   if(tid < TILE / 32) { bitmap[tid] = 0; }
   __syncthreads();
+  uint32_t new_values = 0;   // RA values that differ from their predecessor: the reference's RA run count
   for(uint64_t k = tid; k < j1 - j0; k += IL_THREADS)
   {
     uint64_t j = j0 + k;
-    uint32_t q = (uint32_t)(j + (uint64_t)keys[j - key_base] - d0);
+    KeyT key = keys[j - key_base];
+    uint32_t q = (uint32_t)(j + (uint64_t)key - d0);
     atomicOr(&bitmap[q >> 5], 1u << (q & 31u));
+    new_values += (j == key_base || keys[j - key_base - 1] != key) ? 1u : 0u;
   }
+  if(distinct_keys != nullptr && new_values != 0) { atomicAdd(&distinct, new_values); }
   __syncthreads();
+  if(distinct_keys != nullptr && tid == 0 && distinct != 0) { atomicAdd(distinct_keys, (unsigned long long)distinct); }
   if(tid < 32)
   {
     uint32_t local[4], sum = 0;
@@ -654,25 +662,26 @@ uint64_t interleave_tile_size() { return TILE; }
 
 template<class KeyT>
 int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
-                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream)
+                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream,
+                    unsigned long long* d_distinct_keys)
 {
   if(p1 <= p0) { return BWTM_OK; }
   uint64_t tiles = div_up(p1 - p0, TILE);
   k4_partition<KeyT><<<(unsigned)div_up(tiles + 1, 256), 256, 0, stream>>>(d_keys, key_base, key_count, p0, p1, tiles, d_tile_j);
   BWTM_LAUNCH_CHECK();
-  k4_interleave<KeyT><<<(unsigned)tiles, IL_THREADS, 0, stream>>>(device_view(a), device_view(b), d_keys, key_base, d_tile_j, p0, p1, d_merged);
+  k4_interleave<KeyT><<<(unsigned)tiles, IL_THREADS, 0, stream>>>(device_view(a), device_view(b), d_keys, key_base, d_tile_j, p0, p1, d_merged, d_distinct_keys);
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }
 
-template int interleave_slab<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t);
-template int interleave_slab<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t);
+template int interleave_slab<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t, unsigned long long*);
+template int interleave_slab<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t, unsigned long long*);
 
 template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
                      uint64_t begin, uint64_t end, uint64_t slab_symbols,
                      OutputBuffer* out, EncodeControl* d_control, bool finish,
-                     float* interleave_ms, float* encode_ms, cudaStream_t stream)
+                     float* interleave_ms, float* encode_ms, cudaStream_t stream, unsigned long long* d_distinct_keys)
 {
   slab_symbols = clamp_slab(slab_symbols, end - begin);
   uint64_t max_tiles = slab_symbols / TILE;
@@ -687,7 +696,7 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
   {
     uint64_t p1 = std::min(p0 + slab_symbols, end);
     timer.start();
-    BWTM_TRY(interleave_slab<KeyT>(a, b, d_keys, key_base, key_count, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream));
+    BWTM_TRY(interleave_slab<KeyT>(a, b, d_keys, key_base, key_count, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream, d_distinct_keys));
     *interleave_ms += timer.stop();
 
     timer.start();
@@ -705,33 +714,13 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
 }
 
 template int interleave_range<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
-                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t);
+                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t, unsigned long long*);
 template int interleave_range<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
-                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t);
+                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t, unsigned long long*);
 
 //------------------------------------------------------------------------------
 
 int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } return (n == 0 ? 1 : n); }
-
-// Number of distinct values of a sorted array: the reference's RA run count (support.h:421-428).
-template<class KeyT>
-__global__ void __launch_bounds__(256)
-count_distinct(const KeyT* __restrict__ keys, uint64_t n, unsigned long long* __restrict__ result)
-{
-  __shared__ unsigned int block_total;
-  if(threadIdx.x == 0) { block_total = 0; }
-  __syncthreads();
-  unsigned int local = 0;
-  for(uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += (uint64_t)gridDim.x * blockDim.x)
-  {
-    local += (k == 0 || keys[k] != keys[k - 1]) ? 1u : 0u;
-  }
-#pragma unroll
-  for(int offset = 16; offset > 0; offset >>= 1) { local += __shfl_down_sync(0xFFFFFFFFu, local, offset); }
-  if((threadIdx.x & 31) == 0 && local != 0) { atomicAdd(&block_total, local); }
-  __syncthreads();
-  if(threadIdx.x == 0 && block_total != 0) { atomicAdd(result, (unsigned long long)block_total); }
-}
 
 // Wraps freshly encoded RLE bytes into an index (K0 unless skipped). `counts` (6 values) are the
 // expected per-comp counts, or NULL.
@@ -994,16 +983,8 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   }
   if(sorted == keys.as<KeyT>()) { alt.release(); } else { keys.release(); }
 
-  {
-    DeviceBuffer distinct; BWTM_TRY(distinct.allocate(sizeof(unsigned long long)));
-    BWTM_CUDA(cudaMemsetAsync(distinct.ptr, 0, sizeof(unsigned long long), stream));
-    count_distinct<KeyT><<<(unsigned)std::min<uint64_t>(div_up(n_b, 256), 148 * 16), 256, 0, stream>>>(sorted, n_b, distinct.as<unsigned long long>());
-    BWTM_LAUNCH_CHECK();
-    unsigned long long runs = 0;
-    BWTM_CUDA(cudaMemcpyAsync(&runs, distinct.ptr, sizeof(runs), cudaMemcpyDeviceToHost, stream));
-    BWTM_CUDA(cudaStreamSynchronize(stream));
-    timings->ra_runs = runs;
-  }
+  DeviceBuffer distinct; BWTM_TRY(distinct.allocate(sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemsetAsync(distinct.ptr, 0, sizeof(unsigned long long), stream));
 
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
@@ -1013,7 +994,8 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   if(rc == BWTM_OK)
   {
     rc = interleave_range<KeyT>(a, b, sorted, 0, n_b, 0, a->size + b->size, options->slab_symbols,
-                                &out, control.as<EncodeControl>(), true, &interleave_ms, &encode_ms, stream);
+                                &out, control.as<EncodeControl>(), true, &interleave_ms, &encode_ms, stream,
+                                distinct.as<unsigned long long>());
   }
   if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   timings->interleave_seconds = interleave_ms * 1e-3;
@@ -1022,6 +1004,11 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
 
   EncodeControl ctl;
   BWTM_CUDA(cudaMemcpy(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost));
+  {
+    unsigned long long ra_runs = 0;
+    BWTM_CUDA(cudaMemcpy(&ra_runs, distinct.ptr, sizeof(ra_runs), cudaMemcpyDeviceToHost));
+    timings->ra_runs = ra_runs;
+  }
   timings->merged_runs = ctl.runs_total;
   timings->merged_bytes = ctl.out_size;
 

@@ -111,13 +111,14 @@ int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_optio
 // K4 for one slab: merged symbols of positions [p0, p1) into `merged` (tile_j: (p1 - p0) / 4096 + 2 entries).
 template<class KeyT>
 int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
-                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream);
+                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream,
+                    unsigned long long* d_distinct_keys = nullptr);
 uint64_t interleave_tile_size();
 
 template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
                      uint64_t begin, uint64_t end, uint64_t slab_symbols,
                      OutputBuffer* out, EncodeControl* d_control, bool finish,
-                     float* interleave_ms, float* encode_ms, cudaStream_t stream);
+                     float* interleave_ms, float* encode_ms, cudaStream_t stream, unsigned long long* d_distinct_keys = nullptr);
 
 } // namespace bwtm

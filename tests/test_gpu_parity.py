@@ -98,6 +98,7 @@ def test_merge_bit_exact(oracle, shape, slab):
     assert np.array_equal(M.counts(), want.counts()) and M.sequences() == want.sequences and M.size() == want.size
     assert M.hash() == want.hash()
     assert M.timings.ra_values == B.size
+    assert M.timings.ra_runs == len(oracle.sort_compress(oracle.build_ra_dfs(A, B)))   # the reference's RA run count
     # definition: the merge is the BWT of A's reads followed by B's reads
     direct = oracle.bwt_of_reads([r for r in ra] + [r for r in rb])
     assert np.array_equal(M.extract(), direct)
