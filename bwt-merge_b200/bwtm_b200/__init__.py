@@ -48,7 +48,8 @@ class MergeOptions(C.Structure):
     """bwtm_merge_options: MergeParameters (fmi.h:45-80) plus device knobs."""
     _fields_ = [("run_buffer_size", C.c_uint64), ("thread_buffer_size", C.c_uint64), ("merge_buffers", C.c_uint64),
                 ("threads", C.c_uint64), ("sequence_blocks", C.c_uint64), ("temp_dir", C.c_char_p),
-                ("slab_symbols", C.c_uint64), ("keep_inputs", C.c_uint32), ("skip_index", C.c_uint32)]
+                ("slab_symbols", C.c_uint64), ("keep_inputs", C.c_uint32), ("skip_index", C.c_uint32),
+                ("host_output", C.c_void_p), ("host_output_capacity", C.c_uint64)]
 
 
 class Timings(C.Structure):
@@ -152,6 +153,7 @@ class MergeParameters:
         self.temp_dir = "."
         self.slab_symbols = 0
         self.skip_index = False
+        self.host_output = None      # numpy uint8 array (ideally page-locked): receives the merged RLE bytes while encoding
 
     def setRB(self, mb): self.run_buffer_size = mb * 1048576 // 16
     def setTB(self, mb): self.thread_buffer_size = mb * 1048576
@@ -166,6 +168,8 @@ class MergeParameters:
         o.merge_buffers = self.merge_buffers; o.threads = self.threads; o.sequence_blocks = self.sequence_blocks
         o.temp_dir = self.temp_dir.encode(); o.slab_symbols = self.slab_symbols
         o.keep_inputs = 1 if keep_inputs else 0; o.skip_index = 1 if self.skip_index else 0
+        if self.host_output is not None:
+            o.host_output = self.host_output.ctypes.data; o.host_output_capacity = self.host_output.nbytes
         return o
 
 

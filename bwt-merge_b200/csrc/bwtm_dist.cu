@@ -354,7 +354,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   EncodeControl ctl;
   BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  OutputBuffer out = { nullptr, 0, ctl.out_size };
+  OutputBuffer out = { nullptr, 0, ctl.out_size, nullptr };
   uint64_t estimate = (a->rle_bytes + b->rle_bytes) / G;
   int rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream);
   timer.start();
@@ -404,7 +404,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   BWTM_CUDA(cudaStreamSynchronize(stream));
   uint64_t total_bytes = slices[(size_t)3 * (G - 1)] + slices[(size_t)3 * (G - 1) + 1];
   timings->merged_bytes = total_bytes; timings->merged_runs = slices[(size_t)3 * (G - 1) + 2];
-  OutputBuffer full = { nullptr, 0, 0 };
+  OutputBuffer full = { nullptr, 0, 0, nullptr };
   rc = ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream);
   if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   for(int k = 0; k < G; k++)

@@ -397,9 +397,62 @@ int ensure_capacity(OutputBuffer* out, uint64_t needed, uint64_t valid_bytes, cu
     BWTM_CUDA(cudaMemcpyAsync(bigger.ptr, out->ptr, valid_bytes, cudaMemcpyDeviceToDevice, stream));
     BWTM_CUDA(cudaStreamSynchronize(stream));
   }
+  if(out->sink != nullptr) { BWTM_CUDA(cudaStreamSynchronize(out->sink->stream)); }   // a copy may still read the old buffer
   device_free(out->ptr);
   out->ptr = static_cast<uint8_t*>(bigger.detach());
   out->capacity = capacity;
+  return BWTM_OK;
+}
+
+// Device-driven copy into page-locked host memory (accessible through unified addressing). Unlike a DMA copy
+// it does not occupy the copy engine, which the encoder's small read-backs of the following slab need.
+__global__ void __launch_bounds__(256)
+copy_to_host(uint8_t* __restrict__ host, const uint8_t* __restrict__ device, uint64_t bytes)
+{
+  uint64_t head = (16 - (reinterpret_cast<uintptr_t>(device) & 15)) & 15;
+  if(head > bytes) { head = bytes; }
+  uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, threads = (uint64_t)gridDim.x * blockDim.x;
+  if(((reinterpret_cast<uintptr_t>(host) + head) & 15) != 0)   // differently aligned: byte copy
+  {
+    for(uint64_t i = tid; i < bytes; i += threads) { host[i] = device[i]; }
+    return;
+  }
+  for(uint64_t i = tid; i < head; i += threads) { host[i] = device[i]; }
+  uint64_t vectors = (bytes - head) / 16;
+  const uint4* src = reinterpret_cast<const uint4*>(device + head);
+  uint4* dst = reinterpret_cast<uint4*>(host + head);
+  for(uint64_t i = tid; i < vectors; i += threads) { dst[i] = src[i]; }
+  for(uint64_t i = head + vectors * 16 + tid; i < bytes; i += threads) { host[i] = device[i]; }
+}
+
+int flush_to_host(OutputBuffer* out, const EncodeControl* d_control, cudaStream_t stream)
+{
+  HostSink* sink = out->sink;
+  if(sink == nullptr) { return BWTM_OK; }
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  uint64_t final_bytes = ctl.out_size - out->origin;
+  if(final_bytes <= sink->copied) { return BWTM_OK; }
+  if(final_bytes > sink->capacity)
+  {
+    set_error("host output buffer too small: %llu bytes needed so far, capacity %llu",
+              (unsigned long long)final_bytes, (unsigned long long)sink->capacity);
+    return BWTM_ERR_CAPACITY;
+  }
+  BWTM_CUDA(cudaEventRecord(sink->ready, stream));
+  BWTM_CUDA(cudaStreamWaitEvent(sink->stream, sink->ready, 0));
+  if(sink->device_visible)
+  {
+    copy_to_host<<<64, 256, 0, sink->stream>>>(sink->ptr + sink->copied, out->ptr + sink->copied, final_bytes - sink->copied);
+    BWTM_LAUNCH_CHECK();
+  }
+  else
+  {
+    BWTM_CUDA(cudaMemcpyAsync(sink->ptr + sink->copied, out->ptr + sink->copied, final_bytes - sink->copied,
+                              cudaMemcpyDeviceToHost, sink->stream));
+  }
+  sink->copied = final_bytes;
   return BWTM_OK;
 }
 
@@ -702,6 +755,7 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
     timer.start();
     BWTM_TRY(encoder.encode(merged.as<uint8_t>(), p1 - p0, out, d_control, stream));
     *encode_ms += timer.stop();
+    BWTM_TRY(flush_to_host(out, d_control, stream));
   }
 
   if(finish)
@@ -709,6 +763,7 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
     timer.start();
     BWTM_TRY(encoder.finish(out, d_control, stream));
     *encode_ms += timer.stop();
+    BWTM_TRY(flush_to_host(out, d_control, stream));
   }
   return BWTM_OK;
 }
@@ -731,7 +786,7 @@ int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, 
   BWTM_CUDA(cudaMemcpyAsync(exact.ptr, out->ptr, rle_bytes, cudaMemcpyDeviceToDevice, stream));
   BWTM_CUDA(cudaMemsetAsync(exact.as<uint8_t>() + rle_bytes, 0, RLE_PADDING, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  device_free(out->ptr); out->ptr = nullptr; out->capacity = 0;
+  if(out->sink == nullptr) { device_free(out->ptr); out->ptr = nullptr; out->capacity = 0; }   // else a host copy may still read it
 
   if(!skip_index)
   {
@@ -771,7 +826,7 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   SlabEncoder encoder; BWTM_TRY(encoder.init(slab, stream));
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
-  OutputBuffer buffer = { nullptr, 0, 0 };
+  OutputBuffer buffer = { nullptr, 0, 0, nullptr };
   int rc = ensure_capacity(&buffer, n / 4 + (1 << 20), 0, stream);
   for(uint64_t p0 = 0; rc == BWTM_OK && p0 < n; p0 += slab)
   {
@@ -988,7 +1043,26 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
 
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
-  OutputBuffer out = { nullptr, 0, 0 };
+  OutputBuffer out = { nullptr, 0, 0, nullptr };
+  HostSink sink = { options->host_output, options->host_output_capacity, 0, nullptr, nullptr, false };
+  if(options->host_output != nullptr)
+  {
+    cudaPointerAttributes attributes;
+    if(cudaPointerGetAttributes(&attributes, options->host_output) == cudaSuccess && attributes.type == cudaMemoryTypeHost)
+    {
+      sink.device_visible = true;   // page-locked: kernels can write it directly
+    }
+    cudaGetLastError();
+    BWTM_CUDA(cudaStreamCreateWithFlags(&sink.stream, cudaStreamNonBlocking));
+    BWTM_CUDA(cudaEventCreateWithFlags(&sink.ready, cudaEventDisableTiming));
+    out.sink = &sink;
+  }
+  auto close_sink = [&]()
+  {
+    if(sink.stream != nullptr) { cudaStreamSynchronize(sink.stream); cudaStreamDestroy(sink.stream); sink.stream = nullptr; }
+    if(sink.ready != nullptr) { cudaEventDestroy(sink.ready); sink.ready = nullptr; }
+    out.sink = nullptr;
+  };
   int rc = ensure_capacity(&out, a->rle_bytes + b->rle_bytes + ((a->rle_bytes + b->rle_bytes) >> 2) + (1 << 20), 0, stream);
   float interleave_ms = 0.0f, encode_ms = 0.0f;
   if(rc == BWTM_OK)
@@ -997,7 +1071,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
                                 &out, control.as<EncodeControl>(), true, &interleave_ms, &encode_ms, stream,
                                 distinct.as<unsigned long long>());
   }
-  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  if(rc != BWTM_OK) { close_sink(); device_free(out.ptr); return rc; }
   timings->interleave_seconds = interleave_ms * 1e-3;
   timings->encode_seconds = encode_ms * 1e-3;
   keys.release(); alt.release();
@@ -1016,8 +1090,9 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   uint64_t counts[SIGMA];
   for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
   rc = finish_index(&out, ctl.out_size, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
-  device_free(out.ptr);
   timings->index_seconds = timer.stop() * 1e-3;
+  close_sink();              // the last part of the streaming download overlaps the index build
+  device_free(out.ptr);
   return rc;
 }
 

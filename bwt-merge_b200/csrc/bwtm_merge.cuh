@@ -43,13 +43,28 @@ struct EncodeControl
 // the sorted RA values `keys` (keys[j - key_base] is the RA value of b's position j), run detection
 // and the byte-exact writer.  Appends to *d_out (grown when needed); the encoder state lives in
 // d_control (device) and crosses calls.  `finish` flushes the pending run.
+// Optional host destination that receives finished output bytes while later slabs are still being encoded.
+struct HostSink
+{
+  uint8_t*     ptr;
+  uint64_t     capacity;
+  uint64_t     copied;     // bytes already queued for copying
+  cudaStream_t stream;     // non-blocking copy stream
+  cudaEvent_t  ready;
+  bool         device_visible;   // page-locked host memory: copied by a kernel instead of the DMA engine
+};
+
 struct OutputBuffer
 {
   uint8_t* ptr;
   uint64_t capacity;
   uint64_t origin;     // global byte offset of ptr[0]: a GPU slice of the output starts where the previous slice ended
+  HostSink* sink;      // may be null
   uint8_t* at_origin() const { return ptr - origin; }   // kernels index this with global offsets
 };
+
+// Queues the copy of all finished bytes (below the writer's current offset) to the sink.
+int flush_to_host(OutputBuffer* out, const EncodeControl* d_control, cudaStream_t stream);
 
 // CUDA-event stopwatch on one stream.
 struct EventTimer

@@ -78,6 +78,11 @@ typedef struct
   uint64_t slab_symbols;           /* merged positions interleaved per pass (default 2^30) */
   uint32_t keep_inputs;            /* 0: a and b are destroyed by bwtm_merge, as the reference does */
   uint32_t skip_index;             /* 1: do not build the rank structure of the result (RLE only) */
+  /* Streaming download (single-GPU merge): if host_output is not NULL the merged RLE bytes are also copied into
+     it, overlapped with the encoding of later parts (use page-locked memory). host_output_capacity must hold
+     the whole result, else BWTM_ERR_CAPACITY. The byte count is bwtm_timings.merged_bytes. */
+  uint8_t* host_output;
+  uint64_t host_output_capacity;
 } bwtm_merge_options;
 
 /* Per-stage device timings of the last merge (CUDA events), the GPU counterpart of the

@@ -291,3 +291,19 @@ def test_pipelined_walk_and_sort(oracle, monkeypatch, chunks):
     ra = _variable_reads(rng, g, 200, 1, 300); rb = _variable_reads(rng, g, 150, 1, 300)
     A, B = oracle.from_comps(oracle.bwt_of_reads(ra)), oracle.from_comps(oracle.bwt_of_reads(rb))
     assert np.array_equal(FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle())).rle(), oracle.merge(A, B).rle())
+
+
+@pytest.mark.parametrize("slab", [0, 4096])
+def test_streaming_download(oracle, slab):
+    """options.host_output: the merged bytes arrive in the host buffer while later slabs are encoded."""
+    ra, bwt_a, rb, bwt_b = collections(oracle, "reads")
+    A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+    want = oracle.merge(A, B).rle()
+    p = MergeParameters(); p.slab_symbols = slab; p.host_output = np.zeros(len(want) + 100, dtype=np.uint8)
+    M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+    assert M.timings.merged_bytes == len(want)
+    assert np.array_equal(p.host_output[:len(want)], want) and np.array_equal(M.rle(), want)
+    p.host_output = np.zeros(len(want) - 1, dtype=np.uint8)      # too small: refused, not truncated
+    with pytest.raises(bwtm_b200.BwtmError) as err:
+        FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+    assert err.value.code == -5
