@@ -323,31 +323,63 @@ void index_free(bwtm_index* index)
   delete index;
 }
 
-int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t stream, bwtm_index** out)
+// Plane words of 32 consecutive symbols held one per byte (the interleave's output): bit i of plane k is
+// bit k of symbol i. Four symbols of a 32-bit word are gathered with one multiply.
+__global__ void k0_planes_from_symbols(const uint8_t* __restrict__ symbols, uint64_t first_position, uint64_t count,
+                                       uint4* __restrict__ records)
 {
-  if(rle_bytes == 0) { set_error("empty BWT"); return BWTM_ERR_ARGUMENT; }
-  uint64_t blocks = div_up(rle_bytes, RLE_BLOCK);
+  uint64_t chunk = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(chunk * 32 >= count) { return; }
+  uint32_t planes[3] = { 0, 0, 0 };
+  uint64_t remaining = count - chunk * 32;
+  if(remaining < 32)   // the ragged end of the sequence: nothing is read or set past it
+  {
+    for(uint32_t i = 0; i < (uint32_t)remaining; i++)
+    {
+      uint32_t value = symbols[chunk * 32 + i];
+      planes[0] |= (value & 1u) << i; planes[1] |= ((value >> 1) & 1u) << i; planes[2] |= ((value >> 2) & 1u) << i;
+    }
+    records[(first_position >> 5) + chunk] = make_uint4(planes[0], planes[1], planes[2], 0);
+    return;
+  }
+  const uint4* src = reinterpret_cast<const uint4*>(symbols + chunk * 32);
+  uint4 lo = src[0], hi = src[1];
+  uint32_t w[8] = { lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w };
+#pragma unroll
+  for(int j = 0; j < 8; j++)
+  {
+#pragma unroll
+    for(int k = 0; k < 3; k++)
+    {
+      uint32_t nibble = ((((w[j] >> k) & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+      planes[k] |= nibble << (4 * j);
+    }
+  }
+  records[(first_position >> 5) + chunk] = make_uint4(planes[0], planes[1], planes[2], 0);
+}
 
-  DeviceBuffer starts; BWTM_TRY(starts.allocate((blocks + 1) * sizeof(uint64_t)));
-  BWTM_TRY(rle_block_starts(d_rle, rle_bytes, starts.as<uint64_t>(), stream));
-  uint64_t size = 0;
-  BWTM_CUDA(cudaMemcpy(&size, starts.as<uint64_t>() + blocks, sizeof(uint64_t), cudaMemcpyDeviceToHost));
-  if(size == 0) { set_error("BWT decodes to an empty sequence"); return BWTM_ERR_ARGUMENT; }
+int planes_from_symbols(const uint8_t* d_symbols, uint64_t first_position, uint64_t count, uint4* d_records, cudaStream_t stream)
+{
+  if(count == 0) { return BWTM_OK; }
+  if((first_position & 31) != 0) { set_error("slab not aligned to 32 positions"); return BWTM_ERR_INTERNAL; }
+  uint64_t chunks = div_up(count, 32);
+  k0_planes_from_symbols<<<(unsigned)div_up(chunks, 256), 256, 0, stream>>>(d_symbols, first_position, count, d_records);
+  BWTM_LAUNCH_CHECK();
+  return BWTM_OK;
+}
 
+// Second half of K0: per-record counts, their scans, headers and the superblock table, for records whose
+// planes are filled. Takes ownership of d_rle and d_records on success.
+int index_from_planes(uint8_t* d_rle, uint64_t rle_bytes, uint4* d_records, uint64_t size, cudaStream_t stream, bwtm_index** out)
+{
   uint64_t n_records = (size >> RECORD_SHIFT) + 1;
   uint64_t n_super = ((n_records - 1) >> SUPER_RECORD_SHIFT) + 1;
-  DeviceBuffer records; BWTM_TRY(records.allocate(n_records * 64));
   DeviceBuffer super; BWTM_TRY(super.allocate(n_super * SUPER_STRIDE * sizeof(uint64_t)));
-  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, n_records * 64, stream));
   BWTM_CUDA(cudaMemsetAsync(super.ptr, 0, n_super * SUPER_STRIDE * sizeof(uint64_t), stream));
-
-  k0_fill_planes<<<(unsigned)div_up(blocks, K0_THREADS), K0_THREADS, 0, stream>>>(
-    d_rle, rle_bytes, blocks, starts.as<uint64_t>(), records.as<uint32_t>());
-  BWTM_LAUNCH_CHECK();
 
   DeviceBuffer counts; BWTM_TRY(counts.allocate(5 * n_records * sizeof(uint32_t)));
   DeviceBuffer cumulative; BWTM_TRY(cumulative.allocate(5 * n_records * sizeof(uint64_t)));
-  k0_record_counts<<<(unsigned)div_up(n_records, 256), 256, 0, stream>>>(records.as<uint4>(), n_records, counts.as<uint32_t>());
+  k0_record_counts<<<(unsigned)div_up(n_records, 256), 256, 0, stream>>>(d_records, n_records, counts.as<uint32_t>());
   BWTM_LAUNCH_CHECK();
 
   size_t temp_bytes = 0;
@@ -364,7 +396,7 @@ int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t strea
   }
 
   k0_pack_headers<<<(unsigned)div_up(n_records, 256), 256, 0, stream>>>(
-    records.as<uint32_t>(), n_records, cumulative.as<uint64_t>(), super.as<uint64_t>());
+    reinterpret_cast<uint32_t*>(d_records), n_records, cumulative.as<uint64_t>(), super.as<uint64_t>());
   BWTM_LAUNCH_CHECK();
 
   // Totals: exclusive prefix of the last record + its own counts.
@@ -388,11 +420,34 @@ int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t strea
   index->sequences = index->counts[0];
   index->C[0] = 0;
   for(int c = 0; c < SIGMA; c++) { index->C[c + 1] = index->C[c] + index->counts[c]; }
-  index->device_bytes = rle_bytes + RLE_PADDING + records.bytes + super.bytes;
+  index->device_bytes = rle_bytes + RLE_PADDING + n_records * 64 + super.bytes;
   index->d_rle = d_rle;
-  index->d_records = static_cast<uint4*>(records.detach());
+  index->d_records = d_records;
   index->d_super = static_cast<uint64_t*>(super.detach());
   *out = index;
+  return BWTM_OK;
+}
+
+int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t stream, bwtm_index** out)
+{
+  if(rle_bytes == 0) { set_error("empty BWT"); return BWTM_ERR_ARGUMENT; }
+  uint64_t blocks = div_up(rle_bytes, RLE_BLOCK);
+
+  DeviceBuffer starts; BWTM_TRY(starts.allocate((blocks + 1) * sizeof(uint64_t)));
+  BWTM_TRY(rle_block_starts(d_rle, rle_bytes, starts.as<uint64_t>(), stream));
+  uint64_t size = 0;
+  BWTM_CUDA(cudaMemcpy(&size, starts.as<uint64_t>() + blocks, sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  if(size == 0) { set_error("BWT decodes to an empty sequence"); return BWTM_ERR_ARGUMENT; }
+
+  uint64_t n_records = (size >> RECORD_SHIFT) + 1;
+  DeviceBuffer records; BWTM_TRY(records.allocate(n_records * 64));
+  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, n_records * 64, stream));
+  k0_fill_planes<<<(unsigned)div_up(blocks, K0_THREADS), K0_THREADS, 0, stream>>>(
+    d_rle, rle_bytes, blocks, starts.as<uint64_t>(), records.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  starts.release();
+  BWTM_TRY(index_from_planes(d_rle, rle_bytes, records.as<uint4>(), size, stream, out));
+  records.detach();
   return BWTM_OK;
 }
 

@@ -58,6 +58,10 @@ struct DeviceBuffer
 // Index construction from RLE bytes already on the device. Takes ownership of d_rle on success.
 int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t stream, bwtm_index** out);
 void index_free(bwtm_index* index);
+// The same when the plane words of the records are already filled (headers zero): skips the run decoding.
+int index_from_planes(uint8_t* d_rle, uint64_t rle_bytes, uint4* d_records, uint64_t size, cudaStream_t stream, bwtm_index** out);
+// Fills the plane words of the records covering [first_position, first_position + count) from one-symbol-per-byte data.
+int planes_from_symbols(const uint8_t* d_symbols, uint64_t first_position, uint64_t count, uint4* d_records, cudaStream_t stream);
 
 // Per-64-byte-block symbol counts and their exclusive scan (block start positions).
 int rle_block_starts(const uint8_t* d_rle, uint64_t rle_bytes, uint64_t* d_starts /* blocks + 1 */, cudaStream_t stream);

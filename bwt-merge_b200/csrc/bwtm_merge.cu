@@ -734,7 +734,8 @@ template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
                      uint64_t begin, uint64_t end, uint64_t slab_symbols,
                      OutputBuffer* out, EncodeControl* d_control, bool finish,
-                     float* interleave_ms, float* encode_ms, cudaStream_t stream, unsigned long long* d_distinct_keys)
+                     float* interleave_ms, float* encode_ms, cudaStream_t stream, unsigned long long* d_distinct_keys,
+                     uint4* d_result_records)
 {
   slab_symbols = clamp_slab(slab_symbols, end - begin);
   uint64_t max_tiles = slab_symbols / TILE;
@@ -750,6 +751,8 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
     uint64_t p1 = std::min(p0 + slab_symbols, end);
     timer.start();
     BWTM_TRY(interleave_slab<KeyT>(a, b, d_keys, key_base, key_count, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream, d_distinct_keys));
+    // The rank structure of the result takes its plane words straight from the merged symbols.
+    if(d_result_records != nullptr) { BWTM_TRY(planes_from_symbols(merged.as<uint8_t>(), p0, p1 - p0, d_result_records, stream)); }
     *interleave_ms += timer.stop();
 
     timer.start();
@@ -769,9 +772,9 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
 }
 
 template int interleave_range<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
-                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t, unsigned long long*);
+                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t, unsigned long long*, uint4*);
 template int interleave_range<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint64_t,
-                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t, unsigned long long*);
+                                        OutputBuffer*, EncodeControl*, bool, float*, float*, cudaStream_t, unsigned long long*, uint4*);
 
 //------------------------------------------------------------------------------
 
@@ -780,7 +783,7 @@ int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } retu
 // Wraps freshly encoded RLE bytes into an index (K0 unless skipped). `counts` (6 values) are the
 // expected per-comp counts, or NULL.
 int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
-                        cudaStream_t stream, bwtm_index** result)
+                 cudaStream_t stream, bwtm_index** result, DeviceBuffer* filled_records, uint64_t size)
 {
   DeviceBuffer exact; BWTM_TRY(exact.allocate(rle_bytes + RLE_PADDING));
   BWTM_CUDA(cudaMemcpyAsync(exact.ptr, out->ptr, rle_bytes, cudaMemcpyDeviceToDevice, stream));
@@ -790,7 +793,12 @@ int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, 
 
   if(!skip_index)
   {
-    BWTM_TRY(index_from_device_rle(exact.as<uint8_t>(), rle_bytes, stream, result));
+    if(filled_records != nullptr && filled_records->ptr != nullptr)
+    {
+      BWTM_TRY(index_from_planes(exact.as<uint8_t>(), rle_bytes, filled_records->as<uint4>(), size, stream, result));
+      filled_records->detach();
+    }
+    else { BWTM_TRY(index_from_device_rle(exact.as<uint8_t>(), rle_bytes, stream, result)); }
     exact.detach();
     bwtm_index* m = *result;
     for(int c = 0; counts != nullptr && c < SIGMA; c++)
@@ -828,9 +836,19 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
   OutputBuffer buffer = { nullptr, 0, 0, nullptr };
   int rc = ensure_capacity(&buffer, n / 4 + (1 << 20), 0, stream);
+  // The records take their plane words from the symbols when those can be read 32 at a time.
+  DeviceBuffer records;
+  if((reinterpret_cast<uintptr_t>(d_symbols) & 15) == 0 && (slab & 31) == 0)
+  {
+    uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
+    BWTM_TRY(records.allocate(record_bytes));
+    BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
+  }
   for(uint64_t p0 = 0; rc == BWTM_OK && p0 < n; p0 += slab)
   {
-    rc = encoder.encode(d_symbols + p0, std::min(slab, n - p0), &buffer, control.as<EncodeControl>(), stream);
+    uint64_t count = std::min(slab, n - p0);
+    rc = encoder.encode(d_symbols + p0, count, &buffer, control.as<EncodeControl>(), stream);
+    if(rc == BWTM_OK && records.ptr != nullptr) { rc = planes_from_symbols(d_symbols + p0, p0, count, records.as<uint4>(), stream); }
   }
   if(rc == BWTM_OK) { rc = encoder.finish(&buffer, control.as<EncodeControl>(), stream); }
   EncodeControl ctl;
@@ -838,7 +856,7 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   {
     set_error("cannot read the encoder state"); rc = BWTM_ERR_CUDA;
   }
-  if(rc == BWTM_OK) { rc = finish_index(&buffer, ctl.out_size, nullptr, 0, false, stream, out); }
+  if(rc == BWTM_OK) { rc = finish_index(&buffer, ctl.out_size, nullptr, 0, false, stream, out, &records, n); }
   device_free(buffer.ptr);
   return rc;
 }
@@ -1065,11 +1083,20 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   };
   int rc = ensure_capacity(&out, a->rle_bytes + b->rle_bytes + ((a->rle_bytes + b->rle_bytes) >> 2) + (1 << 20), 0, stream);
   float interleave_ms = 0.0f, encode_ms = 0.0f;
+  // Records of the result: their plane words are filled slab by slab from the merged symbols, so K0 does
+  // not have to decode the bytes K5 has just written. BWTM_RLE_INDEX=1 keeps the decoding route (tests).
+  DeviceBuffer records;
+  if(rc == BWTM_OK && options->skip_index == 0 && getenv("BWTM_RLE_INDEX") == nullptr)
+  {
+    uint64_t record_bytes = (((a->size + b->size) >> RECORD_SHIFT) + 1) * 64;
+    rc = records.allocate(record_bytes);
+    if(rc == BWTM_OK && cudaMemsetAsync(records.ptr, 0, record_bytes, stream) != cudaSuccess) { set_error("cannot clear the records"); rc = BWTM_ERR_CUDA; }
+  }
   if(rc == BWTM_OK)
   {
     rc = interleave_range<KeyT>(a, b, sorted, 0, n_b, 0, a->size + b->size, options->slab_symbols,
                                 &out, control.as<EncodeControl>(), true, &interleave_ms, &encode_ms, stream,
-                                distinct.as<unsigned long long>());
+                                distinct.as<unsigned long long>(), records.as<uint4>());
   }
   if(rc != BWTM_OK) { close_sink(); device_free(out.ptr); return rc; }
   timings->interleave_seconds = interleave_ms * 1e-3;
@@ -1089,7 +1116,8 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   timer.start();
   uint64_t counts[SIGMA];
   for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
-  rc = finish_index(&out, ctl.out_size, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
+  rc = finish_index(&out, ctl.out_size, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result,
+                    &records, a->size + b->size);
   timings->index_seconds = timer.stop() * 1e-3;
   close_sink();              // the last part of the streaming download overlaps the index build
   device_free(out.ptr);

@@ -117,7 +117,7 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
 
 // Wraps encoded RLE bytes (out->ptr[0 .. rle_bytes)) into an index; frees the buffer. counts may be NULL unless skip_index.
 int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
-                 cudaStream_t stream, bwtm_index** result);
+                 cudaStream_t stream, bwtm_index** result, DeviceBuffer* filled_records = nullptr, uint64_t size = 0);
 int bit_length_host(uint64_t v);
 
 int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
@@ -134,6 +134,7 @@ template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
                      uint64_t begin, uint64_t end, uint64_t slab_symbols,
                      OutputBuffer* out, EncodeControl* d_control, bool finish,
-                     float* interleave_ms, float* encode_ms, cudaStream_t stream, unsigned long long* d_distinct_keys = nullptr);
+                     float* interleave_ms, float* encode_ms, cudaStream_t stream, unsigned long long* d_distinct_keys = nullptr,
+                     uint4* d_result_records = nullptr);
 
 } // namespace bwtm

@@ -307,3 +307,31 @@ def test_streaming_download(oracle, slab):
     with pytest.raises(bwtm_b200.BwtmError) as err:
         FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
     assert err.value.code == -5
+
+
+@pytest.mark.parametrize("slab", [0, 4096, 12288])
+def test_result_index_from_merged_symbols(oracle, monkeypatch, slab):
+    """The result's rank structure is filled from the merged symbols; it must equal the one decoded from the
+    encoded bytes (BWTM_RLE_INDEX=1) and answer like the reference's BWT::rank / FMI::LF (bwt.cpp:318-341)."""
+    for shape in ("reads", "noisy_N", "repeats"):
+        ra, bwt_a, rb, bwt_b = collections(oracle, shape)
+        A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+        want = oracle.merge(A, B)
+        p = MergeParameters(); p.slab_symbols = slab
+        fast = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+        monkeypatch.setenv("BWTM_RLE_INDEX", "1")
+        slow = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+        monkeypatch.delenv("BWTM_RLE_INDEX")
+        n = fast.size()
+        assert n == slow.size() == want.size and fast.sequences() == slow.sequences()
+        positions = np.unique(np.concatenate([np.arange(min(n + 1, 300)), np.arange(max(0, n - 300), n + 1),
+                                              np.random.default_rng(3).integers(0, n + 1, 2000)])).astype(np.uint64)
+        for c in range(6):
+            comps = np.full(len(positions), c, dtype=np.uint8)
+            got = fast.rank(positions, comps)
+            assert np.array_equal(got, slow.rank(positions, comps)), (shape, slab, c)
+            assert np.array_equal(got, np.array([want.rank(int(i), c) for i in positions], dtype=np.uint64)), (shape, c)
+        inside = positions[positions < n]
+        assert all(np.array_equal(x, y) for x, y in zip(fast.LF(inside), slow.LF(inside)))
+        assert np.array_equal(fast.extract(0, n), want.decode())
+        assert fast.hash() == slow.hash() == want.hash()
