@@ -14,6 +14,12 @@
 //
 // There is no collective in the search itself. NCCL is loaded with dlopen so that single-GPU users do not
 // need it.
+//
+// The two bulk exchanges (RA values, output slices) do not go through NCCL's staged send/recv: every rank
+// owns two peer windows (cudaMalloc + CUDA IPC, opened once by all other ranks and kept in the communicator)
+// and the senders store straight into the receiver's window over NVLink, one pass and no bounce buffer.
+// NCCL carries the small control traffic (counts, writer state, barriers) and remains the fallback for
+// the bulk data when IPC mappings are not available (BWTM_NCCL_EXCHANGE=1 forces it).
 #include <dlfcn.h>
 
 #include <algorithm>
@@ -91,10 +97,21 @@ int nccl_failed(ncclResult_t result, const char* what)
 
 } // namespace
 
+// Device memory of this rank that every other rank of the communicator has mapped.
+struct PeerWindow
+{
+  uint8_t* local = nullptr;
+  uint64_t capacity = 0;            // identical on all ranks
+  std::vector<uint8_t*> mapped;     // mapped[p]: rank p's window in this process (mapped[rank] == local)
+};
+
 struct bwtm_comm
 {
   ncclComm_t comm;
   int        rank, world;
+  int        peer_state;            // 0 not tried yet, 1 windows usable, -1 not available: NCCL moves the data
+  PeerWindow key_window, rle_window;
+  unsigned long long* d_flag;       // scratch of the barrier
 };
 
 namespace bwtm
@@ -148,6 +165,101 @@ static int merge_sorted_pieces(KeyT* src, KeyT* dst, std::vector<uint64_t> offse
   }
   BWTM_CUDA(cudaStreamSynchronize(stream));
   *result = src;
+  return BWTM_OK;
+}
+
+// All ranks reach this point of their streams before any of them goes on: a one-word all-reduce.
+static int stream_barrier(bwtm_comm* comm, cudaStream_t stream)
+{
+  BWTM_NCCL(nccl()->AllReduce(comm->d_flag, comm->d_flag, 1, ncclUint64, ncclMax, comm->comm, stream));
+  return BWTM_OK;
+}
+
+static void window_close(bwtm_comm* comm, PeerWindow* window)
+{
+  for(int p = 0; p < (int)window->mapped.size(); p++)
+  {
+    if(p != comm->rank && window->mapped[p] != nullptr) { cudaIpcCloseMemHandle(window->mapped[p]); }
+  }
+  window->mapped.clear();
+}
+
+struct WindowTicket { cudaIpcMemHandle_t handle; unsigned long long ok; };
+
+// Collective: makes `window` at least `need` bytes on every rank (all ranks pass the same value) and maps
+// it everywhere. *usable is false when the windows cannot be used; nothing is left half-open in that case.
+static int window_reserve(bwtm_comm* comm, PeerWindow* window, uint64_t need, cudaStream_t stream, bool* usable)
+{
+  *usable = false;
+  if(comm->peer_state < 0) { return BWTM_OK; }
+  if(need <= window->capacity) { *usable = true; return BWTM_OK; }
+  NcclApi* api = nccl();
+  const int G = comm->world, r = comm->rank;
+
+  // Nobody may free a window that a peer still has mapped.
+  window_close(comm, window);
+  BWTM_TRY(stream_barrier(comm, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  if(window->local != nullptr) { cudaFree(window->local); window->local = nullptr; }
+  window->capacity = 0;
+
+  uint64_t capacity = div_up(need + (need >> 3) + (1ull << 20), 1ull << 21) << 21;
+  WindowTicket mine; std::memset(&mine, 0, sizeof(mine));
+  void* fresh = nullptr;
+  cudaError_t status = cudaMalloc(&fresh, capacity);
+  if(status != cudaSuccess)   // the stream-ordered pool may be sitting on the memory
+  {
+    cudaGetLastError();
+    int device = 0; cudaMemPool_t pool;
+    if(cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) { cudaMemPoolTrimTo(pool, 0); }
+    status = cudaMalloc(&fresh, capacity);
+  }
+  if(status == cudaSuccess && cudaIpcGetMemHandle(&mine.handle, fresh) == cudaSuccess) { mine.ok = 1; }
+  cudaGetLastError();
+
+  std::vector<WindowTicket> tickets(G);
+  DeviceBuffer d_mine, d_all;
+  BWTM_TRY(d_mine.allocate(sizeof(WindowTicket))); BWTM_TRY(d_all.allocate(G * sizeof(WindowTicket)));
+  auto all_agree = [&](bool* everyone) -> int
+  {
+    BWTM_CUDA(cudaMemcpyAsync(d_mine.ptr, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
+    BWTM_NCCL(api->AllGather(d_mine.ptr, d_all.ptr, sizeof(WindowTicket), ncclUint8, comm->comm, stream));
+    BWTM_CUDA(cudaMemcpyAsync(tickets.data(), d_all.ptr, G * sizeof(WindowTicket), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    *everyone = true;
+    for(int p = 0; p < G; p++) { *everyone = *everyone && (tickets[p].ok != 0); }
+    return BWTM_OK;
+  };
+
+  bool everyone = false;
+  BWTM_TRY(all_agree(&everyone));
+  if(everyone)
+  {
+    std::vector<WindowTicket> handles = tickets;
+    window->mapped.assign(G, nullptr);
+    window->mapped[r] = static_cast<uint8_t*>(fresh);
+    for(int p = 0; p < G; p++)
+    {
+      if(p == r) { continue; }
+      void* remote = nullptr;
+      if(cudaIpcOpenMemHandle(&remote, handles[p].handle, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); mine.ok = 0; break; }
+      window->mapped[p] = static_cast<uint8_t*>(remote);
+    }
+    BWTM_TRY(all_agree(&everyone));
+  }
+  if(!everyone)
+  {
+    window_close(comm, window);
+    BWTM_TRY(stream_barrier(comm, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    if(fresh != nullptr) { cudaFree(fresh); }
+    comm->peer_state = -1;
+    if(getenv("BWTM_DEBUG") != nullptr) { fprintf(stderr, "bwtm[%d] peer windows unavailable, using NCCL for the bulk data\n", r); }
+    return BWTM_OK;
+  }
+  window->local = static_cast<uint8_t*>(fresh); window->capacity = capacity;
+  comm->peer_state = 1;
+  *usable = true;
   return BWTM_OK;
 }
 
@@ -214,27 +326,47 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   timer.start();
   auto exchange_start = std::chrono::steady_clock::now();
   const int P = G - 1;
-  std::vector<unsigned long long> lo(std::max(P, 1), 0), hi(std::max(P, 1), n_a + 1), mid(std::max(P, 1), 0), below(std::max(P, 1), 0);
+  std::vector<unsigned long long> lo(std::max(P, 1), 0), hi(std::max(P, 1), n_a + 1);
   DeviceBuffer d_probes, d_counts;
-  BWTM_TRY(d_probes.allocate(std::max(P, 1) * sizeof(unsigned long long)));
-  BWTM_TRY(d_counts.allocate(std::max(P, 1) * sizeof(unsigned long long)));
   std::vector<unsigned long long> target(std::max(P, 1), 0);
   for(int k = 0; k < P; k++) { target[k] = (unsigned long long)(((__uint128_t)(n_a + n_b) * (k + 1)) / G); }
+  // PROBES candidates per splitter and round: five bits of the answer per all-reduce instead of one.
+  const int PROBES = 31;
+  std::vector<unsigned long long> candidates((size_t)std::max(P, 1) * PROBES, 0), counted((size_t)std::max(P, 1) * PROBES, 0);
+  BWTM_TRY(d_probes.allocate(candidates.size() * sizeof(unsigned long long)));
+  BWTM_TRY(d_counts.allocate(candidates.size() * sizeof(unsigned long long)));
   for(int iteration = 0; P > 0 && iteration < 66; iteration++)
   {
     bool open = false;
-    for(int k = 0; k < P; k++) { mid[k] = lo[k] + (hi[k] - lo[k]) / 2; open = open || (lo[k] < hi[k]); }
+    for(int k = 0; k < P; k++)
+    {
+      open = open || (lo[k] < hi[k]);
+      unsigned long long width = hi[k] - lo[k];
+      for(int t = 0; t < PROBES; t++)   // increasing, all in [lo, hi); duplicates are harmless
+      {
+        candidates[(size_t)k * PROBES + t] = lo[k] + (unsigned long long)(((__uint128_t)width * (t + 1)) / (PROBES + 1));
+        if(width > 0 && candidates[(size_t)k * PROBES + t] >= hi[k]) { candidates[(size_t)k * PROBES + t] = hi[k] - 1; }
+      }
+    }
     if(!open) { break; }
-    BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, mid.data(), P * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    lower_bounds<KeyT><<<1, 32, 0, stream>>>(sorted, local_n, d_probes.as<unsigned long long>(), P, d_counts.as<unsigned long long>());
+    const int n_probes = P * PROBES;
+    BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, candidates.data(), n_probes * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    lower_bounds<KeyT><<<div_up(n_probes, 128), 128, 0, stream>>>(sorted, local_n, d_probes.as<unsigned long long>(), n_probes, d_counts.as<unsigned long long>());
     BWTM_LAUNCH_CHECK();
-    BWTM_NCCL(api->AllReduce(d_counts.ptr, d_counts.ptr, P, ncclUint64, ncclSum, comm->comm, stream));
-    BWTM_CUDA(cudaMemcpyAsync(below.data(), d_counts.ptr, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    BWTM_NCCL(api->AllReduce(d_counts.ptr, d_counts.ptr, n_probes, ncclUint64, ncclSum, comm->comm, stream));
+    BWTM_CUDA(cudaMemcpyAsync(counted.data(), d_counts.ptr, n_probes * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     BWTM_CUDA(cudaStreamSynchronize(stream));
     for(int k = 0; k < P; k++)
     {
       if(lo[k] >= hi[k]) { continue; }
-      if(mid[k] + below[k] >= target[k]) { hi[k] = mid[k]; } else { lo[k] = mid[k] + 1; }
+      // p + #{keys < p} is non-decreasing in p: the answer lies after the last candidate that fails.
+      for(int t = 0; t < PROBES; t++)
+      {
+        unsigned long long c = candidates[(size_t)k * PROBES + t];
+        if(c < lo[k]) { continue; }
+        if(c + counted[(size_t)k * PROBES + t] >= target[k]) { hi[k] = c; break; }
+        lo[k] = c + 1;
+      }
     }
   }
   phase.mark("splitter search");
@@ -282,27 +414,62 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   phase.mark("count matrix");
   // 4. all-to-all by A-position range, then 5. local sort of what arrived (G sorted pieces)
   DeviceBuffer received, received_alt;
-  BWTM_TRY(received.allocate(std::max<uint64_t>(recv_total, 1) * sizeof(KeyT)));
-  BWTM_NCCL(api->GroupStart());
-  for(int peer = 0; peer < G; peer++)
+  const bool force_nccl = (getenv("BWTM_NCCL_EXCHANGE") != nullptr);
+  if(force_nccl) { comm->peer_state = -1; }
+  bool direct = false;
+  if(G > 1)
   {
-    if(send_count[peer] > 0) { BWTM_NCCL(api->Send(sorted + send_offset[peer], send_count[peer], NcclKey<KeyT>::type, peer, comm->comm, stream)); }
-    uint64_t incoming = recv_offset[peer + 1] - recv_offset[peer];
-    if(incoming > 0) { BWTM_NCCL(api->Recv(received.as<KeyT>() + recv_offset[peer], incoming, NcclKey<KeyT>::type, peer, comm->comm, stream)); }
+    uint64_t largest = 0;   // every rank knows the whole matrix, so all ask for the same size
+    for(int dst = 0; dst < G; dst++)
+    {
+      uint64_t sum = 0;
+      for(int src = 0; src < G; src++) { sum += matrix[(size_t)src * G + dst]; }
+      largest = std::max(largest, sum);
+    }
+    BWTM_TRY(window_reserve(comm, &(comm->key_window), std::max<uint64_t>(largest, 1) * sizeof(KeyT), stream, &direct));
   }
-  BWTM_NCCL(api->GroupEnd());
+  KeyT* arrived = nullptr;
+  if(direct)
+  {
+    // Every piece goes straight into its place in the owner's window. Rank r starts with peer r + 1 so
+    // that no receiver is the target of two senders at once.
+    for(int step = 0; step < G; step++)
+    {
+      int peer = (r + step) % G;
+      if(send_count[peer] == 0) { continue; }
+      uint64_t offset = 0;
+      for(int src = 0; src < r; src++) { offset += matrix[(size_t)src * G + peer]; }
+      BWTM_CUDA(cudaMemcpyAsync(reinterpret_cast<KeyT*>(comm->key_window.mapped[peer]) + offset, sorted + send_offset[peer],
+                                send_count[peer] * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream));
+    }
+    BWTM_TRY(stream_barrier(comm, stream));   // all pieces have landed everywhere
+    arrived = reinterpret_cast<KeyT*>(comm->key_window.local);
+  }
+  else
+  {
+    BWTM_TRY(received.allocate(std::max<uint64_t>(recv_total, 1) * sizeof(KeyT)));
+    BWTM_NCCL(api->GroupStart());
+    for(int peer = 0; peer < G; peer++)
+    {
+      if(send_count[peer] > 0) { BWTM_NCCL(api->Send(sorted + send_offset[peer], send_count[peer], NcclKey<KeyT>::type, peer, comm->comm, stream)); }
+      uint64_t incoming = recv_offset[peer + 1] - recv_offset[peer];
+      if(incoming > 0) { BWTM_NCCL(api->Recv(received.as<KeyT>() + recv_offset[peer], incoming, NcclKey<KeyT>::type, peer, comm->comm, stream)); }
+    }
+    BWTM_NCCL(api->GroupEnd());
+    arrived = received.as<KeyT>();
+  }
   BWTM_CUDA(cudaStreamSynchronize(stream));
   phase.mark("all-to-all");
   keys.release(); alt.release();
-  KeyT* slice_keys = received.as<KeyT>();
+  KeyT* slice_keys = arrived;
   if(recv_total > 0 && G > 1)
   {
     BWTM_TRY(received_alt.allocate(recv_total * sizeof(KeyT)));
     if(recv_total < 0x7FFFFFFFull)
     {
-      BWTM_TRY(merge_sorted_pieces<KeyT>(received.as<KeyT>(), received_alt.as<KeyT>(), recv_offset, stream, &slice_keys));
+      BWTM_TRY(merge_sorted_pieces<KeyT>(arrived, received_alt.as<KeyT>(), recv_offset, stream, &slice_keys));
     }
-    else { BWTM_TRY(sort_keys<KeyT>(received.as<KeyT>(), received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream)); }
+    else { BWTM_TRY(sort_keys<KeyT>(arrived, received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream)); }
   }
   timings->exchange_seconds = timer.stop() * 1e-3;
   phase.mark("sort received");
@@ -405,14 +572,35 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   uint64_t total_bytes = slices[(size_t)3 * (G - 1)] + slices[(size_t)3 * (G - 1) + 1];
   timings->merged_bytes = total_bytes; timings->merged_runs = slices[(size_t)3 * (G - 1) + 2];
   OutputBuffer full = { nullptr, 0, 0, nullptr };
-  rc = ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream);
-  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  bool direct_gather = false;
+  if(G > 1) { BWTM_TRY(window_reserve(comm, &(comm->rle_window), total_bytes + RLE_PADDING, stream, &direct_gather)); }
   for(int k = 0; k < G; k++)
   {
     uint64_t offset = slices[(size_t)3 * k], bytes = slices[(size_t)3 * k + 1];
-    if(bytes == 0) { continue; }
-    if(offset + bytes > total_bytes) { set_error("inconsistent slice layout"); device_free(out.ptr); device_free(full.ptr); return BWTM_ERR_INTERNAL; }
-    BWTM_NCCL(api->Broadcast(k == r ? (const void*)out.ptr : (const void*)(full.ptr + offset), full.ptr + offset, bytes, ncclUint8, k, comm->comm, stream));
+    if(offset + bytes > total_bytes) { set_error("inconsistent slice layout"); device_free(out.ptr); return BWTM_ERR_INTERNAL; }
+  }
+  if(direct_gather)
+  {
+    // My slice goes to its place in every replica's window, my own included.
+    uint64_t offset = slices[(size_t)3 * r], bytes = slices[(size_t)3 * r + 1];
+    for(int step = 0; bytes > 0 && step < G; step++)
+    {
+      int peer = (r + 1 + step) % G;
+      BWTM_CUDA(cudaMemcpyAsync(comm->rle_window.mapped[peer] + offset, out.ptr, bytes, cudaMemcpyDeviceToDevice, stream));
+    }
+    BWTM_TRY(stream_barrier(comm, stream));
+    full.ptr = comm->rle_window.local; full.capacity = comm->rle_window.capacity; full.borrowed = true;
+  }
+  else
+  {
+    rc = ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream);
+    if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+    for(int k = 0; k < G; k++)
+    {
+      uint64_t offset = slices[(size_t)3 * k], bytes = slices[(size_t)3 * k + 1];
+      if(bytes == 0) { continue; }
+      BWTM_NCCL(api->Broadcast(k == r ? (const void*)out.ptr : (const void*)(full.ptr + offset), full.ptr + offset, bytes, ncclUint8, k, comm->comm, stream));
+    }
   }
   BWTM_CUDA(cudaStreamSynchronize(stream));
   device_free(out.ptr);
@@ -425,7 +613,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   uint64_t counts[SIGMA];
   for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
   rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
-  device_free(full.ptr);
+  if(!full.borrowed) { device_free(full.ptr); }
   timings->index_seconds = timer.stop() * 1e-3;
   phase.mark("index");
   return rc;
@@ -476,6 +664,12 @@ int bwtm_comm_create(const uint8_t* id, int rank, int world, bwtm_comm** out)
   BWTM_NCCL(api->CommInitRank(&comm, world, unique, rank));
   bwtm_comm* c = new bwtm_comm();
   c->comm = comm; c->rank = rank; c->world = world;
+  c->peer_state = 0; c->d_flag = nullptr;
+  if(cudaMalloc(reinterpret_cast<void**>(&(c->d_flag)), sizeof(unsigned long long)) != cudaSuccess || cudaMemset(c->d_flag, 0, sizeof(unsigned long long)) != cudaSuccess)
+  {
+    cudaGetLastError(); api->CommDestroy(comm); delete c;
+    set_error("cannot allocate the barrier word"); return BWTM_ERR_MEMORY;
+  }
   *out = c;
   return BWTM_OK;
 }
@@ -483,6 +677,14 @@ int bwtm_comm_create(const uint8_t* id, int rank, int world, bwtm_comm** out)
 int bwtm_comm_destroy(bwtm_comm* comm)
 {
   if(comm == nullptr) { return BWTM_OK; }
+  // Call it on all ranks once the last merge has returned everywhere (like ncclCommDestroy): the windows
+  // of this rank go away here.
+  cudaDeviceSynchronize();
+  window_close(comm, &(comm->key_window)); window_close(comm, &(comm->rle_window));
+  if(comm->key_window.local != nullptr) { cudaFree(comm->key_window.local); }
+  if(comm->rle_window.local != nullptr) { cudaFree(comm->rle_window.local); }
+  if(comm->d_flag != nullptr) { cudaFree(comm->d_flag); }
+  cudaGetLastError();
   if(nccl()->ok) { nccl()->CommDestroy(comm->comm); }
   delete comm;
   return BWTM_OK;

@@ -789,7 +789,7 @@ int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, 
   BWTM_CUDA(cudaMemcpyAsync(exact.ptr, out->ptr, rle_bytes, cudaMemcpyDeviceToDevice, stream));
   BWTM_CUDA(cudaMemsetAsync(exact.as<uint8_t>() + rle_bytes, 0, RLE_PADDING, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  if(out->sink == nullptr) { device_free(out->ptr); out->ptr = nullptr; out->capacity = 0; }   // else a host copy may still read it
+  if(out->sink == nullptr && !out->borrowed) { device_free(out->ptr); out->ptr = nullptr; out->capacity = 0; }   // else a host copy may still read it
 
   if(!skip_index)
   {

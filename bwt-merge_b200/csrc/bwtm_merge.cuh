@@ -60,6 +60,7 @@ struct OutputBuffer
   uint64_t capacity;
   uint64_t origin;     // global byte offset of ptr[0]: a GPU slice of the output starts where the previous slice ended
   HostSink* sink;      // may be null
+  bool borrowed = false;   // ptr belongs to someone else (a peer window): never freed or grown here
   uint8_t* at_origin() const { return ptr - origin; }   // kernels index this with global offsets
 };
 

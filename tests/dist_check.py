@@ -20,6 +20,25 @@ def main():
     comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
     thr = synth.error_threshold(0.01)
     cases = [(200000, 20000, 100, 0), (200000, 20000, 100, 524288), (200000, 16000, 100, 262144), (50000, 3000, 60, 8192), (3000, 5, 40, 4096), (100, 1, 30, 0)]
+    # Three passes: peer windows sized by the first (largest) case; windows growing from the smallest case up
+    # in a fresh communicator; the NCCL send/recv + broadcast route.
+    runs = [(comm, cases), (None, cases[::-1]), ("nccl", cases[:1] + cases[3:])]
+    for which, (use, todo) in enumerate(runs):
+        if use is None:
+            dist.barrier(); comm.close(); comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
+        elif use == "nccl":
+            dist.barrier(); comm.close(); os.environ["BWTM_NCCL_EXCHANGE"] = "1"
+            comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
+        check_cases(comm, rank, thr, todo)
+    os.environ.pop("BWTM_NCCL_EXCHANGE", None)
+    dist.barrier()
+    if rank == 0:
+        print("dist_check ok: %d ranks, %d cases" % (world, sum(len(todo) for _, todo in runs)))
+    comm.close()
+    dist.destroy_process_group()
+
+
+def check_cases(comm, rank, thr, cases):
     for G, n, L, slab in cases:
         A = FMI.synthetic(G, 42, L, thr, [(1, n)]); B = FMI.synthetic(G, 42, L, thr, [(2, max(1, n // 2))])
         p = MergeParameters(); p.slab_symbols = slab
@@ -34,11 +53,6 @@ def main():
         again = comm.merge(multi, C_, p, keep_inputs=True)
         direct = FMI.synthetic(G, 42, L, thr, [(1, n), (2, max(1, n // 2)), (3, max(1, n // 3))])
         assert np.array_equal(again.rle(), direct.rle()), "rank %d: sequential distributed merge differs" % rank
-    dist.barrier()
-    if rank == 0:
-        print("dist_check ok: %d ranks, %d cases" % (world, len(cases)))
-    comm.close()
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":
