@@ -489,26 +489,26 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   uint64_t n_slabs = div_up(slice, slab);
   bool parallel = (slice > 0 && n_slabs <= MAX_PARALLEL_SLABS);
 
-  DeviceBuffer merged, tile_j, control;
+  DeviceBuffer tile_j, control;
+  std::vector<DeviceBuffer> merged(parallel ? n_slabs : 0);   // plane chunks of every slab, read again by emit()
   std::vector<SlabEncoder> encoders(parallel ? n_slabs : 1);
   BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   float interleave_ms = 0.0f, encode_ms = 0.0f;
   if(parallel)
   {
-    BWTM_TRY(merged.allocate(slab));
     BWTM_TRY(tile_j.allocate((slab / interleave_tile_size() + 2) * sizeof(uint64_t)));
     for(uint64_t k = 0; k < n_slabs; k++)
     {
       uint64_t p0 = begin + k * slab, p1 = std::min(p0 + slab, end);
       BWTM_TRY(encoders[k].init(p1 - p0, stream));
+      BWTM_TRY(merged[k].allocate(div_up(p1 - p0, interleave_tile_size()) * (interleave_tile_size() / 2)));
       timer.start();
-      BWTM_TRY(interleave_slab<KeyT>(a, b, slice_keys, b_lo, recv_total, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream));
+      BWTM_TRY(interleave_slab<KeyT>(a, b, slice_keys, b_lo, recv_total, p0, p1, merged[k].as<uint4>(), tile_j.as<uint64_t>(), stream));
       interleave_ms += timer.stop();
       timer.start();
-      BWTM_TRY(encoders[k].detect(merged.as<uint8_t>(), p1 - p0, stream));
+      BWTM_TRY(encoders[k].detect(merged[k].as<uint4>(), p1 - p0, stream));
       encode_ms += timer.stop();
     }
-    merged.release();
   }
   phase.mark("interleave + runs");
 
@@ -556,7 +556,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   timings->interleave_seconds = interleave_ms * 1e-3;
   timings->encode_seconds = encode_ms * 1e-3;
   received.release(); received_alt.release();
-  encoders.clear();
+  encoders.clear(); merged.clear();
 
   phase.mark("chained writer");
   // 8. every rank gets the complete run-length BWT

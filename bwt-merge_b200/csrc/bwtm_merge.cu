@@ -53,18 +53,25 @@ __global__ void k4_partition(const KeyT* __restrict__ keys, uint64_t key_base, u
   tile_j[t] = key_base + lo;
 }
 
-__device__ __forceinline__ uint32_t fetch_symbol(const DeviceIndex& idx, uint64_t pos, uint64_t& cached_group, uint4& cached)
+// Bits [pos, pos + 16) of the three planes of `idx`, packed 16 bits apart; only the chunks that hold the
+// `count` symbols actually needed are touched.
+__device__ __forceinline__ uint64_t plane_window(const DeviceIndex& idx, uint64_t pos, uint32_t count)
 {
-  uint64_t group = pos >> 5;
-  if(group != cached_group) { cached = __ldg(idx.records + group); cached_group = group; }
-  uint32_t t = (uint32_t)(pos & 31u);
-  return ((cached.x >> t) & 1u) | (((cached.y >> t) & 1u) << 1) | (((cached.z >> t) & 1u) << 2);
+  if(count == 0) { return 0; }
+  uint64_t chunk = pos >> 5; uint32_t shift = (uint32_t)(pos & 31u);
+  uint4 lo = __ldg(idx.records + chunk);
+  uint4 hi = make_uint4(0, 0, 0, 0);
+  if(shift + count > 32) { hi = __ldg(idx.records + chunk + 1); }
+  uint64_t w0 = __funnelshift_r(lo.x, hi.x, shift) & 0xFFFFu;
+  uint64_t w1 = __funnelshift_r(lo.y, hi.y, shift) & 0xFFFFu;
+  uint64_t w2 = __funnelshift_r(lo.z, hi.z, shift) & 0xFFFFu;
+  return w0 | (w1 << 16) | (w2 << 32);
 }
 
 template<class KeyT>
 __global__ void __launch_bounds__(IL_THREADS)
 k4_interleave(DeviceIndex a, DeviceIndex b, const KeyT* __restrict__ keys, uint64_t key_base,
-              const uint64_t* __restrict__ tile_j, uint64_t begin, uint64_t end, uint8_t* __restrict__ merged,
+              const uint64_t* __restrict__ tile_j, uint64_t begin, uint64_t end, uint4* __restrict__ merged,
               unsigned long long* __restrict__ distinct_keys)
 {
   __shared__ uint32_t bitmap[TILE / 32];
@@ -119,21 +126,32 @@ k4_interleave(DeviceIndex a, DeviceIndex b, const KeyT* __restrict__ keys, uint6
   int valid = 0;
   if(d0 + p0 < d1) { uint64_t left = d1 - d0 - p0; valid = (left < (uint64_t)PER_THREAD ? (int)left : PER_THREAD); }
 
-  uint32_t w[4] = { 0, 0, 0, 0 };
-  uint64_t group_a = ~0ull, group_b = ~0ull;
-  uint4 chunk_a = make_uint4(0, 0, 0, 0), chunk_b = make_uint4(0, 0, 0, 0);
+  // The thread's symbols come from consecutive positions of a (flag 0) and of b (flag 1): a 16-bit window of
+  // each source's planes is taken and the bits are dealt out in flag order. The result is the plane-chunk
+  // layout of the rank records (bwtm_common.cuh), so the merged sequence is never stored one symbol per byte.
+  uint32_t from_b = __popc(flags & low_mask(valid));
+  uint64_t window_a = plane_window(a, ia, (uint32_t)valid - from_b), window_b = plane_window(b, jb, from_b);
+  uint64_t dealt = 0;
 #pragma unroll
   for(int s = 0; s < PER_THREAD; s++)
   {
-    if(s < valid)
-    {
-      uint32_t sym;
-      if((flags >> s) & 1u) { sym = fetch_symbol(b, jb, group_b, chunk_b); jb++; }
-      else                  { sym = fetch_symbol(a, ia, group_a, chunk_a); ia++; }
-      w[s >> 2] |= sym << (8 * (s & 3));
-    }
+    uint64_t take_b = (flags >> s) & 1u;
+    uint64_t source = (take_b ? window_b : window_a);
+    dealt |= (source & 0x0000000100010001ull) << s;
+    window_b >>= take_b; window_a >>= (1u - take_b);
   }
-  *reinterpret_cast<uint4*>(merged + (d0 - begin) + p0) = make_uint4(w[0], w[1], w[2], w[3]);
+  if(valid < PER_THREAD) { dealt &= 0x0000000100010001ull * (uint64_t)low_mask(valid); }
+  // Two neighbouring threads hold the halves of one 32-position chunk.
+  uint64_t upper = __shfl_down_sync(0xFFFFFFFFu, dealt, 1);
+  if((tid & 1) == 0 && valid > 0)
+  {
+    uint4 chunk;
+    chunk.x = (uint32_t)(dealt & 0xFFFFu)         | ((uint32_t)(upper & 0xFFFFu) << 16);
+    chunk.y = (uint32_t)((dealt >> 16) & 0xFFFFu) | ((uint32_t)((upper >> 16) & 0xFFFFu) << 16);
+    chunk.z = (uint32_t)((dealt >> 32) & 0xFFFFu) | ((uint32_t)((upper >> 32) & 0xFFFFu) << 16);
+    chunk.w = 0;
+    merged[((d0 - begin) >> 5) + (tid >> 1)] = chunk;
+  }
 }
 
 //------------------------------------------------------------------------------
@@ -193,8 +211,7 @@ __device__ __forceinline__ uint32_t write_run(uint8_t* __restrict__ out, uint64_
 // absorbs the slab's first run when the symbols agree; it is written as soon as the slab shows that it
 // has ended; the slab's last run becomes the new pending run. The runs in between, [1, m - 1), never
 // depend on the pending run: they are the parallel part.
-__global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ start,
-                         uint64_t m, uint8_t* __restrict__ out, int finish)
+__global__ void enc_head(EncodeControl* ctl, const SlabEnds* __restrict__ ends, uint8_t* __restrict__ out, int finish)
 {
   if(blockIdx.x != 0 || threadIdx.x != 0) { return; }
   ctl->start = 1; ctl->count = 0; ctl->n_short = 0; ctl->n_long = 0; ctl->long_bytes = 0;
@@ -208,9 +225,10 @@ __global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, co
     ctl->slab_base = ctl->out_size;
     return;
   }
+  const uint64_t m = ends->runs;
   if(m > 0)
   {
-    if(ctl->carry_len > 0 && sym[0] == ctl->carry_sym) { ctl->carry_len += start[1] - start[0]; }
+    if(ctl->carry_len > 0 && ends->first_sym == ctl->carry_sym) { ctl->carry_len += ends->first_len; }
     else
     {
       if(ctl->carry_len > 0)
@@ -218,44 +236,17 @@ __global__ void enc_head(EncodeControl* ctl, const uint8_t* __restrict__ sym, co
         ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
         ctl->runs_total++;
       }
-      ctl->carry_sym = sym[0]; ctl->carry_len = start[1] - start[0];
+      ctl->carry_sym = ends->first_sym; ctl->carry_len = ends->first_len;
     }
     if(m > 1)
     {
       ctl->out_size += write_run(out, ctl->out_size, ctl->carry_sym, ctl->carry_len);
       ctl->runs_total++;
-      ctl->carry_sym = sym[m - 1]; ctl->carry_len = start[m] - start[m - 1];
+      ctl->carry_sym = ends->last_sym; ctl->carry_len = ends->last_len;
       ctl->count = m - 2;
     }
   }
   ctl->slab_base = ctl->out_size;
-}
-
-// Runs are stored as (symbol, start position in the slab); start[m] = slab length closes the last run.
-struct RunClass   // 1 in the low word for a short run, 1 in the high word for a long run
-{
-  const uint32_t* start;
-  __host__ __device__ __forceinline__ unsigned long long operator()(const uint64_t& k) const
-  {
-    return (start[k + 1] - start[k] < (uint32_t)MAX_RUN ? 1ull : (1ull << 32));
-  }
-};
-using RunClassIterator = cub::TransformInputIterator<unsigned long long, RunClass, cub::CountingInputIterator<uint64_t>>;
-
-__global__ void enc_collect_long(unsigned long long* __restrict__ stats, const uint32_t* __restrict__ start, const unsigned long long* __restrict__ scan,
-                                 uint64_t count, uint32_t* __restrict__ long_list)
-{
-  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(k >= count) { return; }
-  uint32_t length = start[k + 1] - start[k];
-  unsigned long long s = scan[k];
-  bool is_long = (length >= (uint32_t)MAX_RUN);
-  if(is_long) { long_list[s >> 32] = (uint32_t)k; }
-  if(k == count - 1)
-  {
-    stats[0] = (s & 0xFFFFFFFFull) + (is_long ? 0 : 1);   // short runs of the parallel part
-    stats[1] = (s >> 32) + (is_long ? 1 : 0);             // long runs
-  }
 }
 
 // Bytes of a long run at output offset `state` (mod 64), given its natural size (head + full extension):
@@ -275,9 +266,8 @@ __device__ __forceinline__ uint32_t natural_bytes(uint32_t length)   // length >
 // runs. A long run preceded by `before` short runs starts at offset residue (before + q) mod 64, so the maps
 // do not depend on where the slab lands in the output: they are computed before the writer state is known.
 __global__ void __launch_bounds__(64)
-enc_tile_maps(const uint32_t* __restrict__ start, const unsigned long long* __restrict__ scan,
-              const uint32_t* __restrict__ long_list, uint64_t n_long, uint32_t* __restrict__ tile_bytes,
-              uint16_t* __restrict__ checkpoints)
+enc_tile_maps(const uint32_t* __restrict__ long_len, const uint32_t* __restrict__ long_shorts, uint64_t n_long,
+              uint32_t* __restrict__ tile_bytes, uint16_t* __restrict__ checkpoints)
 {
   __shared__ uint32_t s_len[LONG_SUB], s_nat[LONG_SUB], s_before[LONG_SUB];
   uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
@@ -290,10 +280,9 @@ enc_tile_maps(const uint32_t* __restrict__ start, const unsigned long long* __re
     __syncthreads();
     if(threadIdx.x < LONG_SUB && chunk + threadIdx.x < last)
     {
-      uint32_t idx = long_list[chunk + threadIdx.x];
-      uint32_t length = start[idx + 1] - start[idx];
+      uint32_t length = long_len[chunk + threadIdx.x];
       s_len[threadIdx.x] = length; s_nat[threadIdx.x] = natural_bytes(length);
-      s_before[threadIdx.x] = (uint32_t)scan[idx];
+      s_before[threadIdx.x] = long_shorts[chunk + threadIdx.x];
     }
     __syncthreads();
     int count = (int)(last - chunk < (uint64_t)LONG_SUB ? last - chunk : (uint64_t)LONG_SUB);
@@ -344,8 +333,8 @@ enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint6
 
 // One thread per sub-tile of LONG_SUB long runs: starts from the tile's true entry and the checkpoint of
 // that entry residue.
-__global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __restrict__ start, const unsigned long long* __restrict__ scan,
-                                 const uint32_t* __restrict__ long_list, uint64_t n_long,
+__global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __restrict__ long_len, const uint32_t* __restrict__ long_shorts,
+                                 uint64_t n_long,
                                  const unsigned long long* __restrict__ tile_entry, const uint16_t* __restrict__ checkpoints,
                                  uint32_t* __restrict__ long_offset)
 {
@@ -358,27 +347,11 @@ __global__ void enc_long_offsets(const EncodeControl* ctl, const uint32_t* __res
   unsigned long long p = entry + checkpoints[sub * 64 + ((base_state + (uint32_t)entry) & 63u)];
   for(uint64_t k = first; k < last; k++)
   {
-    uint32_t idx = long_list[k];
-    uint32_t length = start[idx + 1] - start[idx];
+    uint32_t length = long_len[k];
     long_offset[k] = (uint32_t)p;
-    uint32_t state = (base_state + (uint32_t)scan[idx] + (uint32_t)p) & 63u;
+    uint32_t state = (base_state + long_shorts[k] + (uint32_t)p) & 63u;
     p += long_run_bytes_fast(length, natural_bytes(length), state);
   }
-}
-
-__global__ void enc_write(const EncodeControl* ctl, const uint8_t* __restrict__ sym, const uint32_t* __restrict__ start,
-                          const unsigned long long* __restrict__ scan, const uint32_t* __restrict__ long_offset,
-                          uint64_t count, uint8_t* __restrict__ out)
-{
-  uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if(k >= count) { return; }
-  unsigned long long s = scan[k];
-  uint64_t longs_before = s >> 32;
-  uint64_t bytes_before = (s & 0xFFFFFFFFull) + (longs_before < ctl->n_long ? (uint64_t)long_offset[longs_before] : ctl->long_bytes);
-  uint64_t offset = ctl->slab_base + bytes_before;
-  uint32_t length = start[k + 1] - start[k], comp = sym[k];
-  if(length < (uint32_t)MAX_RUN) { out[offset] = (uint8_t)(comp + SIGMA * (length - 1)); }
-  else { write_run(out, offset, comp, length); }
 }
 
 //------------------------------------------------------------------------------
@@ -456,183 +429,393 @@ int flush_to_host(OutputBuffer* out, const EncodeControl* d_control, cudaStream_
   return BWTM_OK;
 }
 
-// K3: maximal runs of a symbol array (what the reference's RunBuffer produces, utils.h:121-142).
-// A run starts wherever a symbol differs from its predecessor. Pass 1 counts the run starts of every
-// RUN_TILE-symbol tile, a scan turns the counts into offsets, pass 2 writes (symbol, start) for every run.
-constexpr int RUN_THREADS = 256;
-constexpr int RUN_TILE    = RUN_THREADS * 16;
+// K3 and the run-parallel half of K5, on plane chunks.
+//
+// A maximal run (what the reference's RunBuffer produces, utils.h:121-142) starts wherever a symbol differs
+// from its predecessor: with the three bit planes of 32 positions in one uint4 that is three XORs. Runs are
+// never stored. The slab is cut into tiles of TILE positions (one chunk per thread); a run belongs to the
+// tile it starts in and ends at the next run start, which is in the same chunk, in a later chunk of the
+// tile (block suffix-minimum) or at the first run start of a later tile (suffix-minimum over the tiles).
+// Three passes read the chunks:
+//   run_tile_survey : run starts, first and last start, (short, long) run counts per tile;
+//   enc_collect_long: length and number of preceding short runs of every long run, in order;
+//   enc_write_tiles : the bytes, once the transducer has placed the long runs.
+// (short, long) counts travel packed in one 64-bit word: short low, long high. The first and the last run
+// of the slab interact with the pending run of the writer and are left to enc_head.
+constexpr int      RUN_THREADS = TILE / 32;     // 128
+constexpr int      RUN_WARPS   = RUN_THREADS / 32;
+constexpr uint32_t NO_START    = 0xFFFFFFFFu;
 
-// Bit i of the result is set when symbol i of the 16 differs from the one before it (`previous` for i = 0).
-__device__ __forceinline__ uint32_t run_start_flags(const uint4& q, uint32_t previous)
+__device__ __forceinline__ unsigned long long run_class(uint32_t length)
 {
-  uint32_t w[4] = { q.x, q.y, q.z, q.w };
-  uint32_t flags = 0;
-#pragma unroll
-  for(int j = 0; j < 4; j++)
+  return (length < (uint32_t)MAX_RUN ? 1ull : (1ull << 32));
+}
+
+__device__ __forceinline__ uint32_t chunk_symbol(const uint4& x, uint32_t i)
+{
+  return ((x.x >> i) & 1u) | (((x.y >> i) & 1u) << 1) | (((x.z >> i) & 1u) << 2);
+}
+
+// Run-start flags of the thread's chunk (bit i: slab position 32 * chunk + i starts a maximal run). Must be
+// called by all threads of the block.
+__device__ __forceinline__ uint32_t chunk_start_flags(const uint4* __restrict__ planes, uint64_t chunk, uint64_t n, uint4& x)
+{
+  const bool active = (chunk * 32 < n);
+  x = make_uint4(0, 0, 0, 0);
+  if(active) { x = planes[chunk]; }
+  uint32_t tops = (x.x >> 31) | ((x.y >> 31) << 1) | ((x.z >> 31) << 2);
+  uint32_t previous = __shfl_up_sync(0xFFFFFFFFu, tops, 1);
+  if((threadIdx.x & 31) == 0 && active && chunk > 0)
   {
-    uint32_t shifted = (w[j] << 8) | (j == 0 ? (previous & 0xFFu) : (w[j - 1] >> 24));
-    uint32_t diff = w[j] ^ shifted;
-    uint32_t nonzero = (((diff & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | diff) & 0x80808080u;   // high bit of every differing byte
-    // gather the four high bits into a nibble
-    uint32_t nibble = ((nonzero >> 7) & 1u) | ((nonzero >> 14) & 2u) | ((nonzero >> 21) & 4u) | ((nonzero >> 28) & 8u);
-    flags |= nibble << (4 * j);
+    uint4 q = planes[chunk - 1];
+    previous = (q.x >> 31) | ((q.y >> 31) << 1) | ((q.z >> 31) << 2);
   }
+  uint32_t flags = (x.x ^ ((x.x << 1) | (previous & 1u))) | (x.y ^ ((x.y << 1) | ((previous >> 1) & 1u))) |
+                   (x.z ^ ((x.z << 1) | ((previous >> 2) & 1u)));
+  if(chunk == 0) { flags |= 1u; }
+  if(!active) { return 0; }
+  uint64_t left = n - chunk * 32;
+  if(left < 32) { flags &= low_mask((int)left); }
   return flags;
 }
 
-// Loads the 16 symbols of slot `slot` (zero-padded beyond n) and the symbol before them (0xFF at the start).
-__device__ __forceinline__ uint4 load_symbols16(const uint8_t* __restrict__ symbols, uint64_t n, uint64_t slot, uint32_t& previous, int& valid)
+// First run start after the thread's chunk: the smallest `first` of the later threads of the block, or
+// `after_tile`. `tile_first` gets the smallest `first` of the whole block.
+__device__ __forceinline__ uint32_t tile_next_start(uint32_t first, uint32_t* warp_first, uint32_t after_tile, uint32_t& tile_first)
 {
-  uint64_t first = slot * 16;
-  valid = (first >= n ? 0 : (n - first < 16 ? (int)(n - first) : 16));
-  previous = (first == 0 || first > n ? 0xFFu : (uint32_t)symbols[first - 1]);
-  uint4 q = make_uint4(0, 0, 0, 0);
-  if(valid == 16) { q = *reinterpret_cast<const uint4*>(symbols + first); }
-  else if(valid > 0)
-  {
-    uint32_t w[4] = { 0, 0, 0, 0 };
-    for(int i = 0; i < valid; i++) { w[i >> 2] |= (uint32_t)symbols[first + i] << (8 * (i & 3)); }
-    q = make_uint4(w[0], w[1], w[2], w[3]);
-  }
-  return q;
-}
-
-__global__ void __launch_bounds__(RUN_THREADS)
-run_tile_counts(const uint8_t* __restrict__ symbols, uint64_t n, uint32_t* __restrict__ tile_counts)
-{
-  __shared__ uint32_t warp_sums[RUN_THREADS / 32];
-  uint32_t previous; int valid;
-  uint4 q = load_symbols16(symbols, n, (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x, previous, valid);
-  uint32_t flags = run_start_flags(q, previous) & ((1u << valid) - 1u);
-  uint32_t count = __popc(flags);
-#pragma unroll
-  for(int offset = 16; offset > 0; offset >>= 1) { count += __shfl_down_sync(0xFFFFFFFFu, count, offset); }
-  if((threadIdx.x & 31) == 0) { warp_sums[threadIdx.x >> 5] = count; }
-  __syncthreads();
-  if(threadIdx.x == 0)
-  {
-    uint32_t total = 0;
-    for(int w = 0; w < RUN_THREADS / 32; w++) { total += warp_sums[w]; }
-    tile_counts[blockIdx.x] = total;
-  }
-}
-
-__global__ void __launch_bounds__(RUN_THREADS)
-run_tile_write(const uint8_t* __restrict__ symbols, uint64_t n, const uint32_t* __restrict__ tile_offsets,
-               uint8_t* __restrict__ run_sym, uint32_t* __restrict__ run_start)
-{
-  __shared__ uint32_t warp_sums[RUN_THREADS / 32];
-  uint32_t previous; int valid;
-  uint64_t slot = (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x;
-  uint4 q = load_symbols16(symbols, n, slot, previous, valid);
-  uint32_t flags = run_start_flags(q, previous) & ((1u << valid) - 1u);
-  uint32_t count = __popc(flags);
-  // exclusive prefix of the counts within the block
-  uint32_t inclusive = count;
-  const int lane = threadIdx.x & 31;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t inclusive = first;
 #pragma unroll
   for(int offset = 1; offset < 32; offset <<= 1)
   {
-    uint32_t v = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-    if(lane >= offset) { inclusive += v; }
+    uint32_t other = __shfl_down_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane + offset < 32 && other < inclusive) { inclusive = other; }
   }
-  if(lane == 31) { warp_sums[threadIdx.x >> 5] = inclusive; }
+  uint32_t next = __shfl_down_sync(0xFFFFFFFFu, inclusive, 1);
+  if(lane == 31) { next = NO_START; }
+  if(lane == 0) { warp_first[warp] = inclusive; }
   __syncthreads();
-  uint32_t before = tile_offsets[blockIdx.x] + inclusive - count;
-  for(int w = 0; w < (int)(threadIdx.x >> 5); w++) { before += warp_sums[w]; }
-  uint32_t words[4] = { q.x, q.y, q.z, q.w };
-  while(flags != 0)
+  tile_first = NO_START;
+#pragma unroll
+  for(int w = RUN_WARPS - 1; w >= 0; w--)
   {
-    int i = __ffs(flags) - 1; flags &= flags - 1;
-    run_sym[before] = (uint8_t)(words[i >> 2] >> (8 * (i & 3)));
-    run_start[before] = (uint32_t)(slot * 16 + i);
-    before++;
+    if(w > warp && warp_first[w] < next) { next = warp_first[w]; }
+    if(warp_first[w] < tile_first) { tile_first = warp_first[w]; }
+  }
+  return (next < after_tile ? next : after_tile);
+}
+
+// Exclusive prefix of `value` over the threads of the block; `total` is the block's sum.
+__device__ __forceinline__ unsigned long long tile_prefix(unsigned long long value, unsigned long long* warp_sums, unsigned long long& total)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  unsigned long long inclusive = value;
+#pragma unroll
+  for(int offset = 1; offset < 32; offset <<= 1)
+  {
+    unsigned long long other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane >= offset) { inclusive += other; }
+  }
+  if(lane == 31) { warp_sums[warp] = inclusive; }
+  __syncthreads();
+  unsigned long long before = 0; total = 0;
+#pragma unroll
+  for(int w = 0; w < RUN_WARPS; w++)
+  {
+    if(w < warp) { before += warp_sums[w]; }
+    total += warp_sums[w];
+  }
+  return before + inclusive - value;
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+run_tile_survey(const uint4* __restrict__ planes, uint64_t n, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_first,
+                uint32_t* __restrict__ tile_last, unsigned long long* __restrict__ tile_class, SlabEnds* __restrict__ ends)
+{
+  __shared__ uint32_t warp_first[RUN_WARPS];
+  __shared__ unsigned long long warp_sums[RUN_WARPS];
+  __shared__ uint32_t warp_last[RUN_WARPS];
+  const uint64_t chunk = (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x;
+  const uint32_t base = (uint32_t)(chunk * 32);
+  uint4 x;
+  uint32_t flags = chunk_start_flags(planes, chunk, n, x);
+  uint32_t first = (flags != 0 ? base + (uint32_t)(__ffs(flags) - 1) : NO_START);
+  uint32_t last = (flags != 0 ? base + (uint32_t)(31 - __clz(flags)) : 0u);
+  uint32_t block_first;
+  uint32_t next = tile_next_start(first, warp_first, NO_START, block_first);
+
+  // Runs whose end lies inside the tile; the tile's last run is classified by run_tile_resolve. The
+  // number of run starts rides along in bits 48.. of the packed word (at most TILE per tile).
+  unsigned long long packed = (unsigned long long)__popc(flags) << 48;
+  uint32_t remaining = flags;
+  while(remaining != 0)
+  {
+    uint32_t position = base + (uint32_t)(__ffs(remaining) - 1);
+    remaining &= remaining - 1;
+    uint32_t end = (remaining != 0 ? base + (uint32_t)(__ffs(remaining) - 1) : next);
+    if(end != NO_START && position != 0) { packed += run_class(end - position); }
+  }
+#pragma unroll
+  for(int offset = 16; offset > 0; offset >>= 1)
+  {
+    packed += __shfl_down_sync(0xFFFFFFFFu, packed, offset);
+    uint32_t other = __shfl_down_sync(0xFFFFFFFFu, last, offset);
+    if(other > last) { last = other; }
+  }
+  if((threadIdx.x & 31) == 0) { warp_sums[threadIdx.x >> 5] = packed; warp_last[threadIdx.x >> 5] = last; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    packed = 0; last = 0;
+    for(int w = 0; w < RUN_WARPS; w++) { packed += warp_sums[w]; if(warp_last[w] > last) { last = warp_last[w]; } }
+    uint32_t count = (uint32_t)(packed >> 48);
+    tile_count[blockIdx.x] = count;
+    tile_first[blockIdx.x] = block_first;
+    tile_last[blockIdx.x] = last;
+    // short counts fit 13 bits and long counts 7 bits per tile: unpack into the (low, high) words
+    tile_class[blockIdx.x] = packed & 0x0000FFFFFFFFFFFFull;
+    if(count > 0) { atomicMax(&(ends->last_start), last); }
+  }
+}
+
+// next_first[t] = first run start in the tiles after t (n when there is none). One block; every thread takes
+// a contiguous range of tiles.
+__global__ void __launch_bounds__(1024)
+run_tile_suffix(const uint32_t* __restrict__ tile_first, uint64_t tiles, uint32_t n, uint32_t* __restrict__ next_first)
+{
+  __shared__ uint32_t range_first[1024];
+  const uint64_t per_thread = div_up(tiles, (uint64_t)1024);
+  const uint64_t begin = (uint64_t)threadIdx.x * per_thread;
+  const uint64_t end = (begin + per_thread < tiles ? begin + per_thread : tiles);
+  uint32_t smallest = NO_START;
+  for(uint64_t t = begin; t < end; t++) { uint32_t v = tile_first[t]; if(v < smallest) { smallest = v; } }
+  range_first[threadIdx.x] = smallest;
+  __syncthreads();
+  uint32_t after = n;   // first start in the ranges of the later threads
+  for(int later = threadIdx.x + 1; later < 1024; later++)
+  {
+    if(range_first[later] != NO_START) { after = range_first[later]; break; }
+  }
+  for(uint64_t t = end; t > begin; t--)
+  {
+    next_first[t - 1] = after;
+    uint32_t v = tile_first[t - 1];
+    if(v != NO_START) { after = v; }
+  }
+}
+
+// Classifies the last run of every tile (its end is now known), and describes the first and the last run of
+// the slab for enc_head. tile_count must already be scanned (tile_count[tiles] = number of runs).
+__global__ void run_tile_resolve(const uint4* __restrict__ planes, uint32_t n, uint64_t tiles, const uint32_t* __restrict__ run_base,
+                                 const uint32_t* __restrict__ tile_last, const uint32_t* __restrict__ next_first,
+                                 unsigned long long* __restrict__ tile_class, SlabEnds* __restrict__ ends)
+{
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(t < tiles && run_base[t + 1] > run_base[t])
+  {
+    uint32_t position = tile_last[t];
+    if(position != 0 && position != ends->last_start) { tile_class[t] += run_class(next_first[t] - position); }
+  }
+  if(t != 0) { return; }
+  ends->runs = run_base[tiles];
+  uint4 x = planes[0];
+  ends->first_sym = chunk_symbol(x, 0);
+  uint32_t first_len = next_first[0];
+  if(run_base[1] > 1)   // the second run starts in tile 0: look for the first symbol that differs
+  {
+    for(uint32_t position = 1; position < (uint32_t)TILE; position++)
+    {
+      if((position & 31u) == 0) { x = planes[position >> 5]; }
+      if(chunk_symbol(x, position & 31u) != ends->first_sym) { first_len = position; break; }
+    }
+  }
+  ends->first_len = first_len;
+  uint32_t start = ends->last_start;
+  x = planes[start >> 5];
+  ends->last_sym = chunk_symbol(x, start & 31u);
+  ends->last_len = n - start;
+}
+
+// Common part of the two passes that need every run with its (short, long) prefix.
+struct TileView
+{
+  uint4 x; uint32_t base, flags, next, last_start; unsigned long long before;
+};
+
+__device__ __forceinline__ void tile_view(const uint4* __restrict__ planes, uint64_t n, const uint32_t* __restrict__ next_first,
+                                          const unsigned long long* __restrict__ class_base, const SlabEnds* __restrict__ ends,
+                                          uint32_t* warp_first, unsigned long long* warp_sums, TileView& view)
+{
+  const uint64_t chunk = (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x;
+  view.base = (uint32_t)(chunk * 32);
+  view.flags = chunk_start_flags(planes, chunk, n, view.x);
+  view.last_start = ends->last_start;
+  uint32_t first = (view.flags != 0 ? view.base + (uint32_t)(__ffs(view.flags) - 1) : NO_START);
+  uint32_t block_first;
+  view.next = tile_next_start(first, warp_first, next_first[blockIdx.x], block_first);
+  unsigned long long mine = 0;
+  uint32_t remaining = view.flags;
+  while(remaining != 0)
+  {
+    uint32_t position = view.base + (uint32_t)(__ffs(remaining) - 1);
+    remaining &= remaining - 1;
+    uint32_t end = (remaining != 0 ? view.base + (uint32_t)(__ffs(remaining) - 1) : view.next);
+    if(position != 0 && position != view.last_start) { mine += run_class(end - position); }
+  }
+  unsigned long long total;
+  view.before = class_base[blockIdx.x] + tile_prefix(mine, warp_sums, total);
+}
+
+// Long runs in order: length and number of short runs before each (all the transducer needs).
+__global__ void __launch_bounds__(RUN_THREADS)
+enc_collect_long(const uint4* __restrict__ planes, uint64_t n, const uint32_t* __restrict__ next_first,
+                 const unsigned long long* __restrict__ class_base, const SlabEnds* __restrict__ ends,
+                 uint32_t* __restrict__ long_len, uint32_t* __restrict__ long_shorts)
+{
+  __shared__ uint32_t warp_first[RUN_WARPS];
+  __shared__ unsigned long long warp_sums[RUN_WARPS];
+  if((class_base[blockIdx.x + 1] >> 32) == (class_base[blockIdx.x] >> 32)) { return; }   // no long run starts in this tile
+  TileView view;
+  tile_view(planes, n, next_first, class_base, ends, warp_first, warp_sums, view);
+  unsigned long long before = view.before;
+  uint32_t remaining = view.flags;
+  while(remaining != 0)
+  {
+    uint32_t position = view.base + (uint32_t)(__ffs(remaining) - 1);
+    remaining &= remaining - 1;
+    if(position == 0 || position == view.last_start) { continue; }
+    uint32_t end = (remaining != 0 ? view.base + (uint32_t)(__ffs(remaining) - 1) : view.next);
+    uint32_t length = end - position;
+    if(length >= (uint32_t)MAX_RUN) { long_len[before >> 32] = length; long_shorts[before >> 32] = (uint32_t)before; }
+    before += run_class(length);
+  }
+}
+
+__global__ void __launch_bounds__(RUN_THREADS)
+enc_write_tiles(const EncodeControl* __restrict__ ctl, const uint4* __restrict__ planes, uint64_t n, const uint32_t* __restrict__ next_first,
+                const unsigned long long* __restrict__ class_base, const SlabEnds* __restrict__ ends,
+                const uint32_t* __restrict__ long_offset, uint8_t* __restrict__ out)
+{
+  __shared__ uint32_t warp_first[RUN_WARPS];
+  __shared__ unsigned long long warp_sums[RUN_WARPS];
+  TileView view;
+  tile_view(planes, n, next_first, class_base, ends, warp_first, warp_sums, view);
+  const unsigned long long n_long = ctl->n_long, long_bytes = ctl->long_bytes, slab_base = ctl->slab_base;
+  unsigned long long before = view.before;
+  uint32_t remaining = view.flags;
+  // bytes of the long runs before the next run to write; refreshed only after a long run
+  unsigned long long longs = before >> 32;
+  unsigned long long long_part = (longs < n_long ? (unsigned long long)long_offset[longs] : long_bytes);
+  while(remaining != 0)
+  {
+    uint32_t i = (uint32_t)(__ffs(remaining) - 1);
+    uint32_t position = view.base + i;
+    remaining &= remaining - 1;
+    if(position == 0 || position == view.last_start) { continue; }
+    uint32_t end = (remaining != 0 ? view.base + (uint32_t)(__ffs(remaining) - 1) : view.next);
+    uint32_t length = end - position, comp = chunk_symbol(view.x, i);
+    unsigned long long offset = slab_base + (before & 0xFFFFFFFFull) + long_part;
+    if(length < (uint32_t)MAX_RUN) { out[offset] = (uint8_t)(comp + SIGMA * (length - 1)); before += 1ull; }
+    else
+    {
+      write_run(out, offset, comp, length);
+      before += 1ull << 32;
+      longs = before >> 32;
+      long_part = (longs < n_long ? (unsigned long long)long_offset[longs] : long_bytes);
+    }
   }
 }
 
 int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
 {
   max_symbols = max_symbols_;
-  run_capacity = 0;
-  BWTM_TRY(num_runs.allocate(4 * sizeof(uint64_t)));
+  long_capacity = 0;
+  slab_planes = nullptr; slab_symbols = 0;
   BWTM_TRY(placed.allocate(sizeof(EncodeControl)));
-  uint64_t tiles = div_up(max_symbols, RUN_TILE) + 1;
-  BWTM_TRY(run_tiles.allocate(tiles * sizeof(uint32_t)));
-  size_t tile_temp = 0, scan_temp = 0;
-  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tile_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)tiles, stream));
-  {
-    RunClassIterator classes(cub::CountingInputIterator<uint64_t>(0), RunClass{ nullptr });
-    BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, scan_temp, classes, (unsigned long long*)nullptr, (int64_t)max_symbols, stream));
-  }
-  BWTM_TRY(cub_temp.allocate(std::max(tile_temp, scan_temp)));
+  BWTM_TRY(ends.allocate(sizeof(SlabEnds)));
+  uint64_t tiles = div_up(max_symbols, TILE) + 1;
+  BWTM_TRY(tile_count.allocate(tiles * sizeof(uint32_t)));
+  BWTM_TRY(tile_first.allocate(tiles * sizeof(uint32_t)));
+  BWTM_TRY(tile_last.allocate(tiles * sizeof(uint32_t)));
+  BWTM_TRY(next_first.allocate(tiles * sizeof(uint32_t)));
+  BWTM_TRY(class_base.allocate(tiles * sizeof(unsigned long long)));
+  size_t count_temp = 0, class_temp = 0;
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, count_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)tiles, stream));
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, class_temp, (unsigned long long*)nullptr, (unsigned long long*)nullptr, (int64_t)tiles, stream));
+  BWTM_TRY(cub_temp.allocate(std::max(count_temp, class_temp)));
   return BWTM_OK;
 }
 
-// Work arrays sized by the number of runs of the slab (a fifth of the symbols for read collections), grow-only.
-int SlabEncoder::reserve_runs(uint64_t runs)
+// Work arrays of the transducer, sized by the number of long runs of the slab; grow-only.
+int SlabEncoder::reserve_long(uint64_t long_runs)
 {
-  if(runs <= run_capacity) { return BWTM_OK; }
-  uint64_t capacity = runs + (runs >> 3) + 1024;
-  uint64_t max_long = std::min(capacity, max_symbols / MAX_RUN + 1);
-  uint64_t max_long_tiles = div_up(max_long, LONG_TILE);
-  BWTM_TRY(run_sym.allocate(capacity));
-  BWTM_TRY(run_start.allocate((capacity + 1) * sizeof(uint32_t)));
-  BWTM_TRY(scan.allocate(capacity * sizeof(unsigned long long)));
-  BWTM_TRY(long_list.allocate(max_long * sizeof(uint32_t)));
-  BWTM_TRY(long_offset.allocate(max_long * sizeof(uint32_t)));
-  BWTM_TRY(tile_bytes.allocate(max_long_tiles * 64 * sizeof(uint32_t)));
-  BWTM_TRY(tile_entry.allocate(max_long_tiles * sizeof(unsigned long long)));
-  BWTM_TRY(checkpoints.allocate((max_long / LONG_SUB + 1) * 64 * sizeof(uint16_t)));
-  run_capacity = capacity;
+  if(long_runs <= long_capacity) { return BWTM_OK; }
+  uint64_t capacity = long_runs + (long_runs >> 3) + 1024;
+  uint64_t long_tiles = div_up(capacity, LONG_TILE);
+  BWTM_TRY(long_len.allocate(capacity * sizeof(uint32_t)));
+  BWTM_TRY(long_shorts.allocate(capacity * sizeof(uint32_t)));
+  BWTM_TRY(long_offset.allocate(capacity * sizeof(uint32_t)));
+  BWTM_TRY(tile_bytes.allocate(long_tiles * 64 * sizeof(uint32_t)));
+  BWTM_TRY(tile_entry.allocate(long_tiles * sizeof(unsigned long long)));
+  BWTM_TRY(checkpoints.allocate((capacity / LONG_SUB + 1) * 64 * sizeof(uint16_t)));
+  long_capacity = capacity;
   return BWTM_OK;
 }
 
-// K3 and the state-free half of K5: maximal runs of `symbols` consecutive symbols, and for the runs
-// [1, m - 1) the short/long scan, the compacted long runs and their transducer tile maps.
-int SlabEncoder::detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream)
+// K3 and the state-free half of K5 for `symbols` consecutive symbols given as plane chunks (chunk 0 holds
+// the first symbol in bit 0; bits beyond the last symbol are zero): the maximal runs and, for the runs
+// [1, m - 1), the short/long prefixes, the long runs in order and their transducer tile maps. The chunks
+// must stay valid until emit() has run.
+int SlabEncoder::detect(const uint4* d_planes, uint64_t symbols, cudaStream_t stream)
 {
   detected_runs = 0; part_count = 0; part_short = 0; part_long = 0;
+  slab_planes = d_planes; slab_symbols = symbols;
   if(symbols == 0) { return BWTM_OK; }
   if(symbols > max_symbols) { set_error("slab of %llu symbols exceeds the encoder capacity", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
   size_t temp_bytes = cub_temp.bytes;
-  BWTM_CUDA(cudaMemsetAsync(num_runs.ptr, 0, 4 * sizeof(uint64_t), stream));
-  uint64_t tiles = div_up(symbols, RUN_TILE);
-  run_tile_counts<<<(unsigned)tiles, RUN_THREADS, 0, stream>>>(d_symbols, symbols, run_tiles.as<uint32_t>());
+  const uint64_t tiles = div_up(symbols, TILE);
+  uint32_t* counts = tile_count.as<uint32_t>();
+  unsigned long long* classes = class_base.as<unsigned long long>();
+  BWTM_CUDA(cudaMemsetAsync(ends.ptr, 0, sizeof(SlabEnds), stream));
+  run_tile_survey<<<(unsigned)tiles, RUN_THREADS, 0, stream>>>(d_planes, symbols, counts, tile_first.as<uint32_t>(), tile_last.as<uint32_t>(),
+                                                               classes, ends.as<SlabEnds>());
   BWTM_LAUNCH_CHECK();
-  BWTM_CUDA(cudaMemsetAsync(run_tiles.as<uint32_t>() + tiles, 0, sizeof(uint32_t), stream));
-  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, run_tiles.as<uint32_t>(), run_tiles.as<uint32_t>(), (int64_t)(tiles + 1), stream));
+  BWTM_CUDA(cudaMemsetAsync(counts + tiles, 0, sizeof(uint32_t), stream));
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, counts, counts, (int64_t)(tiles + 1), stream));
   count_launch(2);
-  uint32_t total_runs = 0;
-  BWTM_CUDA(cudaMemcpyAsync(&total_runs, run_tiles.as<uint32_t>() + tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  run_tile_suffix<<<1, 1024, 0, stream>>>(tile_first.as<uint32_t>(), tiles, (uint32_t)symbols, next_first.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  run_tile_resolve<<<(unsigned)div_up(tiles, 256), 256, 0, stream>>>(d_planes, (uint32_t)symbols, tiles, counts, tile_last.as<uint32_t>(),
+                                                                    next_first.as<uint32_t>(), classes, ends.as<SlabEnds>());
+  BWTM_LAUNCH_CHECK();
+  BWTM_CUDA(cudaMemsetAsync(classes + tiles, 0, sizeof(unsigned long long), stream));
+  temp_bytes = cub_temp.bytes;
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, classes, classes, (int64_t)(tiles + 1), stream));
+  count_launch(2);
+
+  uint32_t total_runs = 0; unsigned long long totals = 0;
+  BWTM_CUDA(cudaMemcpyAsync(&total_runs, counts + tiles, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaMemcpyAsync(&totals, classes + tiles, sizeof(totals), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   uint64_t m = total_runs;
   if(m == 0) { set_error("run detection found no runs in %llu symbols", (unsigned long long)symbols); return BWTM_ERR_INTERNAL; }
-  BWTM_TRY(this->reserve_runs(m));
-  run_tile_write<<<(unsigned)tiles, RUN_THREADS, 0, stream>>>(d_symbols, symbols, run_tiles.as<uint32_t>(), run_sym.as<uint8_t>(), run_start.as<uint32_t>());
-  BWTM_LAUNCH_CHECK();
-  uint32_t slab_length = (uint32_t)symbols;
-  BWTM_CUDA(cudaMemcpyAsync(run_start.as<uint32_t>() + m, &slab_length, sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
-  BWTM_CUDA(cudaStreamSynchronize(stream));
   detected_runs = m;
   if(m < 3) { return BWTM_OK; }
-
-  uint64_t count = m - 2;
-  const uint32_t* len = run_start.as<uint32_t>() + 1;   // starts of the parallel part, runs [1, m - 1)
-  unsigned long long* stats = num_runs.as<unsigned long long>() + 1;
-  RunClassIterator classes(cub::CountingInputIterator<uint64_t>(0), RunClass{ len });
-  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, classes, scan.as<unsigned long long>(), (int64_t)count, stream));
-  count_launch(2);
-  enc_collect_long<<<(unsigned)div_up(count, 256), 256, 0, stream>>>(stats, len, scan.as<unsigned long long>(), count, long_list.as<uint32_t>());
-  BWTM_LAUNCH_CHECK();
-  unsigned long long host_stats[2] = { 0, 0 };
-  BWTM_CUDA(cudaMemcpyAsync(host_stats, stats, sizeof(host_stats), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaStreamSynchronize(stream));
-  part_count = count; part_short = host_stats[0]; part_long = host_stats[1];
-  uint64_t long_tiles = div_up(part_long, LONG_TILE);
-  if(long_tiles > 0)
+  part_count = m - 2; part_short = totals & 0xFFFFFFFFull; part_long = totals >> 32;
+  if(part_short + part_long != part_count)
   {
-    enc_tile_maps<<<(unsigned)long_tiles, 64, 0, stream>>>(len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), part_long,
-                                                           tile_bytes.as<uint32_t>(), checkpoints.as<uint16_t>());
+    set_error("run classes (%llu short, %llu long) do not add up to %llu runs", (unsigned long long)part_short,
+              (unsigned long long)part_long, (unsigned long long)part_count);
+    return BWTM_ERR_INTERNAL;
+  }
+  if(part_long > 0)
+  {
+    BWTM_TRY(this->reserve_long(part_long));
+    enc_collect_long<<<(unsigned)tiles, RUN_THREADS, 0, stream>>>(d_planes, symbols, next_first.as<uint32_t>(), classes, ends.as<SlabEnds>(),
+                                                                 long_len.as<uint32_t>(), long_shorts.as<uint32_t>());
+    BWTM_LAUNCH_CHECK();
+    enc_tile_maps<<<(unsigned)div_up(part_long, LONG_TILE), 64, 0, stream>>>(long_len.as<uint32_t>(), long_shorts.as<uint32_t>(), part_long,
+                                                                             tile_bytes.as<uint32_t>(), checkpoints.as<uint16_t>());
     BWTM_LAUNCH_CHECK();
   }
   return BWTM_OK;
@@ -650,7 +833,7 @@ int SlabEncoder::advance(OutputBuffer* out, EncodeControl* d_control, cudaStream
   BWTM_CUDA(cudaStreamSynchronize(stream));
   // Upper bound of what this slab can add: two sequential runs, one byte per short run, 16 per long run.
   BWTM_TRY(ensure_capacity(out, ctl.out_size + 512 + part_short + 16 * part_long, ctl.out_size, stream));
-  enc_head<<<1, 1, 0, stream>>>(d_control, run_sym.as<uint8_t>(), run_start.as<uint32_t>(), m, out->at_origin(), 0);
+  enc_head<<<1, 1, 0, stream>>>(d_control, ends.as<SlabEnds>(), out->at_origin(), 0);
   BWTM_LAUNCH_CHECK();
   if(part_count == 0) { return BWTM_OK; }
   uint64_t long_tiles = div_up(part_long, LONG_TILE);
@@ -660,21 +843,22 @@ int SlabEncoder::advance(OutputBuffer* out, EncodeControl* d_control, cudaStream
   return BWTM_OK;
 }
 
-// Second step: writes the bytes of the parallel part at the offsets fixed by advance().
+// Second step: writes the bytes of the parallel part at the offsets fixed by advance(). The plane chunks
+// given to detect() are read again here.
 int SlabEncoder::emit(OutputBuffer* out, cudaStream_t stream)
 {
   if(detected_runs == 0 || part_count == 0) { return BWTM_OK; }
   const EncodeControl* where = placed.as<EncodeControl>();
-  const uint8_t* sym = run_sym.as<uint8_t>() + 1;
-  const uint32_t* len = run_start.as<uint32_t>() + 1;
   if(part_long > 0)
   {
     enc_long_offsets<<<(unsigned)div_up(div_up(part_long, LONG_SUB), 128), 128, 0, stream>>>(
-      where, len, scan.as<unsigned long long>(), long_list.as<uint32_t>(), part_long,
+      where, long_len.as<uint32_t>(), long_shorts.as<uint32_t>(), part_long,
       tile_entry.as<unsigned long long>(), checkpoints.as<uint16_t>(), long_offset.as<uint32_t>());
     BWTM_LAUNCH_CHECK();
   }
-  enc_write<<<(unsigned)div_up(part_count, 256), 256, 0, stream>>>(where, sym, len, scan.as<unsigned long long>(), long_offset.as<uint32_t>(), part_count, out->at_origin());
+  enc_write_tiles<<<(unsigned)div_up(slab_symbols, TILE), RUN_THREADS, 0, stream>>>(
+    where, slab_planes, slab_symbols, next_first.as<uint32_t>(), class_base.as<unsigned long long>(), ends.as<SlabEnds>(),
+    long_offset.as<uint32_t>(), out->at_origin());
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }
@@ -685,9 +869,9 @@ int SlabEncoder::write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t
   return this->emit(out, stream);
 }
 
-int SlabEncoder::encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
+int SlabEncoder::encode(const uint4* d_planes, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream)
 {
-  BWTM_TRY(this->detect(d_symbols, symbols, stream));
+  BWTM_TRY(this->detect(d_planes, symbols, stream));
   return this->write(out, d_control, stream);
 }
 
@@ -698,7 +882,7 @@ int SlabEncoder::finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_
   BWTM_CUDA(cudaMemcpyAsync(&ctl, d_control, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   BWTM_TRY(ensure_capacity(out, ctl.out_size + 256, ctl.out_size, stream));
-  enc_head<<<1, 1, 0, stream>>>(d_control, nullptr, nullptr, 0, out->at_origin(), 1);
+  enc_head<<<1, 1, 0, stream>>>(d_control, nullptr, out->at_origin(), 1);
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }
@@ -715,7 +899,7 @@ uint64_t interleave_tile_size() { return TILE; }
 
 template<class KeyT>
 int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
-                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream,
+                    uint64_t p0, uint64_t p1, uint4* d_merged, uint64_t* d_tile_j, cudaStream_t stream,
                     unsigned long long* d_distinct_keys)
 {
   if(p1 <= p0) { return BWTM_OK; }
@@ -727,8 +911,8 @@ int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys
   return BWTM_OK;
 }
 
-template int interleave_slab<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t, unsigned long long*);
-template int interleave_slab<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint8_t*, uint64_t*, cudaStream_t, unsigned long long*);
+template int interleave_slab<uint32_t>(const bwtm_index*, const bwtm_index*, const uint32_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint4*, uint64_t*, cudaStream_t, unsigned long long*);
+template int interleave_slab<uint64_t>(const bwtm_index*, const bwtm_index*, const uint64_t*, uint64_t, uint64_t, uint64_t, uint64_t, uint4*, uint64_t*, cudaStream_t, unsigned long long*);
 
 template<class KeyT>
 int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
@@ -740,27 +924,26 @@ int interleave_range(const bwtm_index* a, const bwtm_index* b, const KeyT* d_key
   slab_symbols = clamp_slab(slab_symbols, end - begin);
   uint64_t max_tiles = slab_symbols / TILE;
   DeviceBuffer merged, tile_j;
-  BWTM_TRY(merged.allocate(slab_symbols));
+  // The merged symbols of a slab are plane chunks: written into the records of the result when the caller
+  // provides them (then they already are the rank structure's bit planes), else into a slab-sized scratch.
+  if(d_result_records == nullptr) { BWTM_TRY(merged.allocate(slab_symbols / 2)); }
+  else if((begin & 31) != 0) { set_error("result records need a chunk-aligned range"); return BWTM_ERR_INTERNAL; }
   BWTM_TRY(tile_j.allocate((max_tiles + 2) * sizeof(uint64_t)));
   SlabEncoder encoder;
   BWTM_TRY(encoder.init(slab_symbols, stream));
   EventTimer timer(stream);
-
   for(uint64_t p0 = begin; p0 < end; p0 += slab_symbols)
   {
     uint64_t p1 = std::min(p0 + slab_symbols, end);
+    uint4* planes = (d_result_records != nullptr ? d_result_records + (p0 >> 5) : merged.as<uint4>());
     timer.start();
-    BWTM_TRY(interleave_slab<KeyT>(a, b, d_keys, key_base, key_count, p0, p1, merged.as<uint8_t>(), tile_j.as<uint64_t>(), stream, d_distinct_keys));
-    // The rank structure of the result takes its plane words straight from the merged symbols.
-    if(d_result_records != nullptr) { BWTM_TRY(planes_from_symbols(merged.as<uint8_t>(), p0, p1 - p0, d_result_records, stream)); }
+    BWTM_TRY(interleave_slab<KeyT>(a, b, d_keys, key_base, key_count, p0, p1, planes, tile_j.as<uint64_t>(), stream, d_distinct_keys));
     *interleave_ms += timer.stop();
-
     timer.start();
-    BWTM_TRY(encoder.encode(merged.as<uint8_t>(), p1 - p0, out, d_control, stream));
+    BWTM_TRY(encoder.encode(planes, p1 - p0, out, d_control, stream));
     *encode_ms += timer.stop();
     BWTM_TRY(flush_to_host(out, d_control, stream));
   }
-
   if(finish)
   {
     timer.start();
@@ -836,19 +1019,17 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
   OutputBuffer buffer = { nullptr, 0, 0, nullptr };
   int rc = ensure_capacity(&buffer, n / 4 + (1 << 20), 0, stream);
-  // The records take their plane words from the symbols when those can be read 32 at a time.
+  // Symbols -> plane chunks of the records (the layout the encoder reads), slab by slab.
+  if((reinterpret_cast<uintptr_t>(d_symbols) & 15) != 0) { set_error("symbol array is not 16-byte aligned"); device_free(buffer.ptr); return BWTM_ERR_INTERNAL; }
   DeviceBuffer records;
-  if((reinterpret_cast<uintptr_t>(d_symbols) & 15) == 0 && (slab & 31) == 0)
-  {
-    uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
-    BWTM_TRY(records.allocate(record_bytes));
-    BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
-  }
+  uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
+  BWTM_TRY(records.allocate(record_bytes));
+  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
   for(uint64_t p0 = 0; rc == BWTM_OK && p0 < n; p0 += slab)
   {
     uint64_t count = std::min(slab, n - p0);
-    rc = encoder.encode(d_symbols + p0, count, &buffer, control.as<EncodeControl>(), stream);
-    if(rc == BWTM_OK && records.ptr != nullptr) { rc = planes_from_symbols(d_symbols + p0, p0, count, records.as<uint4>(), stream); }
+    rc = planes_from_symbols(d_symbols + p0, p0, count, records.as<uint4>(), stream);
+    if(rc == BWTM_OK) { rc = encoder.encode(records.as<uint4>() + (p0 >> 5), count, &buffer, control.as<EncodeControl>(), stream); }
   }
   if(rc == BWTM_OK) { rc = encoder.finish(&buffer, control.as<EncodeControl>(), stream); }
   EncodeControl ctl;

@@ -88,23 +88,35 @@ struct EventTimer
 };
 
 // K3 + K5 on a stream of symbol slabs: run detection and the byte-exact Run::write.
+// What the sequential glue (enc_head) needs to know about a slab: its number of maximal runs, and the first
+// and the last of them.
+struct SlabEnds
+{
+  unsigned int runs;
+  unsigned int last_start;      // slab position where the last run starts
+  unsigned int first_sym, first_len, last_sym, last_len;
+};
+
 struct SlabEncoder
 {
   uint64_t max_symbols;
-  uint64_t run_capacity;                        // runs the work arrays can hold
-  DeviceBuffer run_sym, run_start, run_tiles, num_runs, scan, long_list, tile_bytes, tile_entry, long_offset, checkpoints, placed, cub_temp;
+  uint64_t long_capacity;                       // long runs the transducer arrays can hold
+  const uint4* slab_planes;                     // input of the last detect(), read again by emit()
+  uint64_t slab_symbols;
+  DeviceBuffer tile_count, tile_first, tile_last, next_first, class_base, ends, long_len, long_shorts, tile_bytes, tile_entry,
+               long_offset, checkpoints, placed, cub_temp;
   uint64_t detected_runs;                       // result of detect(): maximal runs of the slab
   uint64_t part_count, part_short, part_long;   // its parallel part, runs [1, m - 1)
   int init(uint64_t max_symbols, cudaStream_t stream);
-  int reserve_runs(uint64_t runs);
-  // K3: maximal runs of the slab; independent of the encoder state.
-  int detect(const uint8_t* d_symbols, uint64_t symbols, cudaStream_t stream);
+  int reserve_long(uint64_t long_runs);
+  // K3: maximal runs of the slab given as plane chunks; independent of the encoder state.
+  int detect(const uint4* d_planes, uint64_t symbols, cudaStream_t stream);
   // K5: writes the runs found by detect() continuing from the state in d_control. write = advance + emit:
   // advance() moves the writer state past this slab (sequential, tiny), emit() writes the bytes.
   int advance(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
   int emit(OutputBuffer* out, cudaStream_t stream);
   int write(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
-  int encode(const uint8_t* d_symbols, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
+  int encode(const uint4* d_planes, uint64_t symbols, OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
   int finish(OutputBuffer* out, EncodeControl* d_control, cudaStream_t stream);
 };
 
@@ -124,10 +136,11 @@ int bit_length_host(uint64_t v);
 int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
                 bwtm_index** result, bwtm_timings* timings);
 
-// K4 for one slab: merged symbols of positions [p0, p1) into `merged` (tile_j: (p1 - p0) / 4096 + 2 entries).
+// K4 for one slab: merged symbols of positions [p0, p1) as plane chunks, 16 bytes per 32 positions, chunk 0 at
+// d_merged[0] ((p1 - p0) / 32 rounded up chunks; tile_j: (p1 - p0) / 4096 + 2 entries).
 template<class KeyT>
 int interleave_slab(const bwtm_index* a, const bwtm_index* b, const KeyT* d_keys, uint64_t key_base, uint64_t key_count,
-                    uint64_t p0, uint64_t p1, uint8_t* d_merged, uint64_t* d_tile_j, cudaStream_t stream,
+                    uint64_t p0, uint64_t p1, uint4* d_merged, uint64_t* d_tile_j, cudaStream_t stream,
                     unsigned long long* d_distinct_keys = nullptr);
 uint64_t interleave_tile_size();
 
