@@ -186,22 +186,23 @@ __device__ __forceinline__ uint32_t long_run_bytes(uint64_t length, uint32_t sta
 }
 
 // Writes the run at absolute output offset `offset`; returns the bytes written.
-__device__ __forceinline__ uint32_t write_run(uint8_t* __restrict__ out, uint64_t offset, uint32_t comp, uint64_t length)
+// The byte of output offset x goes to out[x - origin] (origin != 0: a staging buffer for part of the output).
+__device__ __forceinline__ uint32_t write_run(uint8_t* __restrict__ out, uint64_t offset, uint32_t comp, uint64_t length, uint64_t origin = 0)
 {
   uint64_t pos = offset;
   while(length > 0)
   {
-    if(length < (uint64_t)MAX_RUN) { out[pos++] = (uint8_t)(comp + SIGMA * (length - 1)); break; }
+    if(length < (uint64_t)MAX_RUN) { out[pos++ - origin] = (uint8_t)(comp + SIGMA * (length - 1)); break; }
     uint32_t remaining = RLE_BLOCK - (uint32_t)(pos & 63u);
     uint32_t basic = (remaining > 1 ? MAX_RUN : MAX_RUN - 1);
-    out[pos++] = (uint8_t)(comp + SIGMA * (basic - 1)); length -= basic; remaining--;
+    out[pos++ - origin] = (uint8_t)(comp + SIGMA * (basic - 1)); length -= basic; remaining--;
     if(remaining > 0)
     {
       uint64_t extension = length;
       if(bytecode_length(extension) > remaining) { extension = (1ull << (7 * remaining)) - 1; }
       length -= extension;
-      while(extension > 0x7Fu) { out[pos++] = (uint8_t)((extension & 0x7Fu) | 0x80u); extension >>= 7; }
-      out[pos++] = (uint8_t)extension;
+      while(extension > 0x7Fu) { out[pos++ - origin] = (uint8_t)((extension & 0x7Fu) | 0x80u); extension >>= 7; }
+      out[pos++ - origin] = (uint8_t)extension;
     }
   }
   return (uint32_t)(pos - offset);
@@ -253,6 +254,9 @@ __global__ void enc_head(EncodeControl* ctl, const SlabEnds* __restrict__ ends, 
 // the natural encoding is used whenever it fits into the rest of the block (support.h:267-280).
 __device__ __forceinline__ uint32_t long_run_bytes_fast(uint32_t length, uint32_t natural, uint32_t state)
 {
+  // Lengths 42..169 (head + one extension byte) are nearly all of the long runs. With one byte left in the
+  // block the head carries 41 symbols and the rest starts a new block: one more byte, or head + extension.
+  if(natural == 2) { return 2u + ((state == 63u && length >= 2u * MAX_RUN - 1u) ? 1u : 0u); }
   return (RLE_BLOCK - state >= natural ? natural : long_run_bytes(length, state));
 }
 
@@ -528,6 +532,31 @@ __device__ __forceinline__ unsigned long long tile_prefix(unsigned long long val
   return before + inclusive - value;
 }
 
+// Runs of one chunk. A run of MAX_RUN or more symbols that starts in a 32-position chunk extends beyond it,
+// so only the last start of a chunk can be a long run: every other start is a short run whose length is the
+// distance to the next start. Nothing loops over runs to classify them.
+struct ChunkRuns
+{
+  uint4 x; uint32_t base, flags, live, top, next; bool long_here;
+  // live: starts that belong to the parallel part; top: bit of the chunk's last start; next: first start after the chunk
+  __device__ __forceinline__ unsigned long long classes() const
+  {
+    unsigned long long is_long = (long_here ? 1ull : 0ull);
+    return (unsigned long long)__popc(live) - is_long + (is_long << 32);
+  }
+};
+
+// `next` = NO_START means that the end of the chunk's last run is not known yet: it is left out.
+__device__ __forceinline__ void classify_chunk(ChunkRuns& runs, uint32_t last_start)
+{
+  runs.live = runs.flags;
+  runs.top = (runs.flags != 0 ? 31u - (uint32_t)__clz(runs.flags) : 0u);
+  if(runs.base == 0) { runs.live &= ~1u; }                                            // first run of the slab
+  if(last_start - runs.base < 32u) { runs.live &= ~(1u << (last_start - runs.base)); } // last run of the slab
+  if(runs.next == NO_START) { runs.live &= ~(1u << runs.top); }
+  runs.long_here = (((runs.live >> runs.top) & 1u) != 0 && runs.next - (runs.base + runs.top) >= (uint32_t)MAX_RUN);
+}
+
 __global__ void __launch_bounds__(RUN_THREADS)
 run_tile_survey(const uint4* __restrict__ planes, uint64_t n, uint32_t* __restrict__ tile_count, uint32_t* __restrict__ tile_first,
                 uint32_t* __restrict__ tile_last, unsigned long long* __restrict__ tile_class, SlabEnds* __restrict__ ends)
@@ -544,17 +573,13 @@ run_tile_survey(const uint4* __restrict__ planes, uint64_t n, uint32_t* __restri
   uint32_t block_first;
   uint32_t next = tile_next_start(first, warp_first, NO_START, block_first);
 
-  // Runs whose end lies inside the tile; the tile's last run is classified by run_tile_resolve. The
-  // number of run starts rides along in bits 48.. of the packed word (at most TILE per tile).
-  unsigned long long packed = (unsigned long long)__popc(flags) << 48;
-  uint32_t remaining = flags;
-  while(remaining != 0)
-  {
-    uint32_t position = base + (uint32_t)(__ffs(remaining) - 1);
-    remaining &= remaining - 1;
-    uint32_t end = (remaining != 0 ? base + (uint32_t)(__ffs(remaining) - 1) : next);
-    if(end != NO_START && position != 0) { packed += run_class(end - position); }
-  }
+  // Runs whose end lies inside the tile; the tile's last run is classified by run_tile_resolve. The slab's
+  // last run is the last run of its tile, so nothing has to be known about it here. The number of run
+  // starts rides along in bits 48.. of the packed word (at most TILE per tile).
+  ChunkRuns runs;
+  runs.x = x; runs.base = base; runs.flags = flags; runs.next = next;
+  classify_chunk(runs, NO_START);
+  unsigned long long packed = ((unsigned long long)__popc(flags) << 48) + runs.classes();
 #pragma unroll
   for(int offset = 16; offset > 0; offset >>= 1)
   {
@@ -578,30 +603,47 @@ run_tile_survey(const uint4* __restrict__ planes, uint64_t n, uint32_t* __restri
   }
 }
 
-// next_first[t] = first run start in the tiles after t (n when there is none). One block; every thread takes
-// a contiguous range of tiles.
-__global__ void __launch_bounds__(1024)
-run_tile_suffix(const uint32_t* __restrict__ tile_first, uint64_t tiles, uint32_t n, uint32_t* __restrict__ next_first)
+// next_first[t] = first run start in the tiles after t (n when there is none). Starts increase with the
+// tile, so that is the first entry of the next tile that has one: nearly always tile t + 1. Tiles are grouped
+// by GROUP_TILES to bound the search when very long runs leave many tiles without a start.
+constexpr int GROUP_TILES = 1024;
+
+__global__ void __launch_bounds__(256)
+run_group_first(const uint32_t* __restrict__ tile_first, uint64_t tiles, uint32_t* __restrict__ group_first)
 {
-  __shared__ uint32_t range_first[1024];
-  const uint64_t per_thread = div_up(tiles, (uint64_t)1024);
-  const uint64_t begin = (uint64_t)threadIdx.x * per_thread;
-  const uint64_t end = (begin + per_thread < tiles ? begin + per_thread : tiles);
+  __shared__ uint32_t warp_first[8];
   uint32_t smallest = NO_START;
-  for(uint64_t t = begin; t < end; t++) { uint32_t v = tile_first[t]; if(v < smallest) { smallest = v; } }
-  range_first[threadIdx.x] = smallest;
+  for(int k = 0; k < GROUP_TILES / 256; k++)
+  {
+    uint64_t t = (uint64_t)blockIdx.x * GROUP_TILES + k * 256 + threadIdx.x;
+    if(t < tiles) { uint32_t v = tile_first[t]; if(v < smallest) { smallest = v; } }
+  }
+#pragma unroll
+  for(int offset = 16; offset > 0; offset >>= 1)
+  {
+    uint32_t other = __shfl_down_sync(0xFFFFFFFFu, smallest, offset);
+    if(other < smallest) { smallest = other; }
+  }
+  if((threadIdx.x & 31) == 0) { warp_first[threadIdx.x >> 5] = smallest; }
   __syncthreads();
-  uint32_t after = n;   // first start in the ranges of the later threads
-  for(int later = threadIdx.x + 1; later < 1024; later++)
+  if(threadIdx.x == 0)
   {
-    if(range_first[later] != NO_START) { after = range_first[later]; break; }
+    for(int w = 1; w < 8; w++) { if(warp_first[w] < smallest) { smallest = warp_first[w]; } }
+    group_first[blockIdx.x] = smallest;
   }
-  for(uint64_t t = end; t > begin; t--)
-  {
-    next_first[t - 1] = after;
-    uint32_t v = tile_first[t - 1];
-    if(v != NO_START) { after = v; }
-  }
+}
+
+__global__ void run_tile_next(const uint32_t* __restrict__ tile_first, const uint32_t* __restrict__ group_first, uint64_t tiles,
+                              uint32_t n, uint32_t* __restrict__ next_first)
+{
+  uint64_t t = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(t >= tiles) { return; }
+  uint64_t group = t / GROUP_TILES, groups = div_up(tiles, (uint64_t)GROUP_TILES);
+  uint64_t group_end = ((group + 1) * GROUP_TILES < tiles ? (group + 1) * GROUP_TILES : tiles);
+  uint32_t found = NO_START;
+  for(uint64_t u = t + 1; u < group_end && found == NO_START; u++) { found = tile_first[u]; }
+  for(uint64_t g = group + 1; g < groups && found == NO_START; g++) { found = group_first[g]; }
+  next_first[t] = (found == NO_START ? n : found);
 }
 
 // Classifies the last run of every tile (its end is now known), and describes the first and the last run of
@@ -637,33 +679,19 @@ __global__ void run_tile_resolve(const uint4* __restrict__ planes, uint32_t n, u
 }
 
 // Common part of the two passes that need every run with its (short, long) prefix.
-struct TileView
-{
-  uint4 x; uint32_t base, flags, next, last_start; unsigned long long before;
-};
-
-__device__ __forceinline__ void tile_view(const uint4* __restrict__ planes, uint64_t n, const uint32_t* __restrict__ next_first,
-                                          const unsigned long long* __restrict__ class_base, const SlabEnds* __restrict__ ends,
-                                          uint32_t* warp_first, unsigned long long* warp_sums, TileView& view)
+__device__ __forceinline__ unsigned long long tile_view(const uint4* __restrict__ planes, uint64_t n, const uint32_t* __restrict__ next_first,
+                                                        const unsigned long long* __restrict__ class_base, const SlabEnds* __restrict__ ends,
+                                                        uint32_t* warp_first, unsigned long long* warp_sums, ChunkRuns& runs)
 {
   const uint64_t chunk = (uint64_t)blockIdx.x * RUN_THREADS + threadIdx.x;
-  view.base = (uint32_t)(chunk * 32);
-  view.flags = chunk_start_flags(planes, chunk, n, view.x);
-  view.last_start = ends->last_start;
-  uint32_t first = (view.flags != 0 ? view.base + (uint32_t)(__ffs(view.flags) - 1) : NO_START);
+  runs.base = (uint32_t)(chunk * 32);
+  runs.flags = chunk_start_flags(planes, chunk, n, runs.x);
+  uint32_t first = (runs.flags != 0 ? runs.base + (uint32_t)(__ffs(runs.flags) - 1) : NO_START);
   uint32_t block_first;
-  view.next = tile_next_start(first, warp_first, next_first[blockIdx.x], block_first);
-  unsigned long long mine = 0;
-  uint32_t remaining = view.flags;
-  while(remaining != 0)
-  {
-    uint32_t position = view.base + (uint32_t)(__ffs(remaining) - 1);
-    remaining &= remaining - 1;
-    uint32_t end = (remaining != 0 ? view.base + (uint32_t)(__ffs(remaining) - 1) : view.next);
-    if(position != 0 && position != view.last_start) { mine += run_class(end - position); }
-  }
+  runs.next = tile_next_start(first, warp_first, next_first[blockIdx.x], block_first);
+  classify_chunk(runs, ends->last_start);
   unsigned long long total;
-  view.before = class_base[blockIdx.x] + tile_prefix(mine, warp_sums, total);
+  return class_base[blockIdx.x] + tile_prefix(runs.classes(), warp_sums, total);
 }
 
 // Long runs in order: length and number of short runs before each (all the transducer needs).
@@ -675,21 +703,18 @@ enc_collect_long(const uint4* __restrict__ planes, uint64_t n, const uint32_t* _
   __shared__ uint32_t warp_first[RUN_WARPS];
   __shared__ unsigned long long warp_sums[RUN_WARPS];
   if((class_base[blockIdx.x + 1] >> 32) == (class_base[blockIdx.x] >> 32)) { return; }   // no long run starts in this tile
-  TileView view;
-  tile_view(planes, n, next_first, class_base, ends, warp_first, warp_sums, view);
-  unsigned long long before = view.before;
-  uint32_t remaining = view.flags;
-  while(remaining != 0)
+  ChunkRuns runs;
+  unsigned long long before = tile_view(planes, n, next_first, class_base, ends, warp_first, warp_sums, runs);
+  if(runs.long_here)
   {
-    uint32_t position = view.base + (uint32_t)(__ffs(remaining) - 1);
-    remaining &= remaining - 1;
-    if(position == 0 || position == view.last_start) { continue; }
-    uint32_t end = (remaining != 0 ? view.base + (uint32_t)(__ffs(remaining) - 1) : view.next);
-    uint32_t length = end - position;
-    if(length >= (uint32_t)MAX_RUN) { long_len[before >> 32] = length; long_shorts[before >> 32] = (uint32_t)before; }
-    before += run_class(length);
+    long_len[before >> 32] = runs.next - (runs.base + runs.top);
+    long_shorts[before >> 32] = (uint32_t)before + (uint32_t)__popc(runs.live & low_mask((int)runs.top));
   }
 }
+
+// The bytes of a tile are one contiguous piece of the output. They are assembled in shared memory, laid out
+// with the alignment of their destination, and stored 16 bytes at a time.
+constexpr int STAGE_BYTES = 4864;   // a tile of 4096 one-symbol runs, the alignment shift and some long runs
 
 __global__ void __launch_bounds__(RUN_THREADS)
 enc_write_tiles(const EncodeControl* __restrict__ ctl, const uint4* __restrict__ planes, uint64_t n, const uint32_t* __restrict__ next_first,
@@ -698,32 +723,47 @@ enc_write_tiles(const EncodeControl* __restrict__ ctl, const uint4* __restrict__
 {
   __shared__ uint32_t warp_first[RUN_WARPS];
   __shared__ unsigned long long warp_sums[RUN_WARPS];
-  TileView view;
-  tile_view(planes, n, next_first, class_base, ends, warp_first, warp_sums, view);
+  __shared__ __align__(16) uint8_t stage[STAGE_BYTES];
+  ChunkRuns runs;
+  unsigned long long before = tile_view(planes, n, next_first, class_base, ends, warp_first, warp_sums, runs);
   const unsigned long long n_long = ctl->n_long, long_bytes = ctl->long_bytes, slab_base = ctl->slab_base;
-  unsigned long long before = view.before;
-  uint32_t remaining = view.flags;
-  // bytes of the long runs before the next run to write; refreshed only after a long run
-  unsigned long long longs = before >> 32;
-  unsigned long long long_part = (longs < n_long ? (unsigned long long)long_offset[longs] : long_bytes);
+
+  // Output range of the tile, from the prefixes of this tile and of the next one.
+  unsigned long long tile_lo = class_base[blockIdx.x], tile_hi = class_base[blockIdx.x + 1];
+  uint64_t tile_begin = slab_base + (tile_lo & 0xFFFFFFFFull) + ((tile_lo >> 32) < n_long ? (uint64_t)long_offset[tile_lo >> 32] : long_bytes);
+  uint64_t tile_end = slab_base + (tile_hi & 0xFFFFFFFFull) + ((tile_hi >> 32) < n_long ? (uint64_t)long_offset[tile_hi >> 32] : long_bytes);
+  if(tile_end <= tile_begin) { return; }
+  const uint32_t shift = (uint32_t)(reinterpret_cast<uintptr_t>(out + tile_begin) & 15u);
+  const bool staged = (tile_end - tile_begin + shift <= (uint64_t)STAGE_BYTES);
+  uint8_t* target = (staged ? stage : out);
+  const uint64_t origin = (staged ? tile_begin - shift : 0);   // target[x - origin] holds output byte x (wraps harmlessly)
+
+  uint64_t offset = slab_base + (before & 0xFFFFFFFFull) + ((before >> 32) < n_long ? (uint64_t)long_offset[before >> 32] : long_bytes);
+  uint32_t remaining = runs.live;
   while(remaining != 0)
   {
     uint32_t i = (uint32_t)(__ffs(remaining) - 1);
-    uint32_t position = view.base + i;
     remaining &= remaining - 1;
-    if(position == 0 || position == view.last_start) { continue; }
-    uint32_t end = (remaining != 0 ? view.base + (uint32_t)(__ffs(remaining) - 1) : view.next);
-    uint32_t length = end - position, comp = chunk_symbol(view.x, i);
-    unsigned long long offset = slab_base + (before & 0xFFFFFFFFull) + long_part;
-    if(length < (uint32_t)MAX_RUN) { out[offset] = (uint8_t)(comp + SIGMA * (length - 1)); before += 1ull; }
-    else
-    {
-      write_run(out, offset, comp, length);
-      before += 1ull << 32;
-      longs = before >> 32;
-      long_part = (longs < n_long ? (unsigned long long)long_offset[longs] : long_bytes);
-    }
+    uint32_t later = runs.flags & ~low_mask((int)i + 1);
+    uint32_t length = (later != 0 ? (uint32_t)(__ffs(later) - 1) - i : runs.next - (runs.base + i));
+    uint32_t comp = chunk_symbol(runs.x, i);
+    if(length < (uint32_t)MAX_RUN) { target[offset - origin] = (uint8_t)(comp + SIGMA * (length - 1)); offset++; }
+    else { write_run(target, offset, comp, length, origin); }   // the chunk's last run: nothing follows it here
   }
+  if(!staged) { return; }
+  __syncthreads();
+
+  uint8_t* destination = out + tile_begin;
+  const uint32_t bytes = (uint32_t)(tile_end - tile_begin);
+  uint32_t head = (shift == 0 ? 0u : 16u - shift);
+  if(head > bytes) { head = bytes; }
+  const uint32_t vectors = (bytes - head) / 16;
+  if(threadIdx.x < head) { destination[threadIdx.x] = stage[shift + threadIdx.x]; }
+  const uint4* staged_vectors = reinterpret_cast<const uint4*>(stage + shift + head);
+  uint4* destination_vectors = reinterpret_cast<uint4*>(destination + head);
+  for(uint32_t v = threadIdx.x; v < vectors; v += RUN_THREADS) { destination_vectors[v] = staged_vectors[v]; }
+  const uint32_t done = head + vectors * 16;
+  if(threadIdx.x < bytes - done) { destination[done + threadIdx.x] = stage[shift + done + threadIdx.x]; }
 }
 
 int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
@@ -738,6 +778,7 @@ int SlabEncoder::init(uint64_t max_symbols_, cudaStream_t stream)
   BWTM_TRY(tile_first.allocate(tiles * sizeof(uint32_t)));
   BWTM_TRY(tile_last.allocate(tiles * sizeof(uint32_t)));
   BWTM_TRY(next_first.allocate(tiles * sizeof(uint32_t)));
+  BWTM_TRY(group_first.allocate((tiles / GROUP_TILES + 1) * sizeof(uint32_t)));
   BWTM_TRY(class_base.allocate(tiles * sizeof(unsigned long long)));
   size_t count_temp = 0, class_temp = 0;
   BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, count_temp, (uint32_t*)nullptr, (uint32_t*)nullptr, (int64_t)tiles, stream));
@@ -783,7 +824,10 @@ int SlabEncoder::detect(const uint4* d_planes, uint64_t symbols, cudaStream_t st
   BWTM_CUDA(cudaMemsetAsync(counts + tiles, 0, sizeof(uint32_t), stream));
   BWTM_CUDA(cub::DeviceScan::ExclusiveSum(cub_temp.ptr, temp_bytes, counts, counts, (int64_t)(tiles + 1), stream));
   count_launch(2);
-  run_tile_suffix<<<1, 1024, 0, stream>>>(tile_first.as<uint32_t>(), tiles, (uint32_t)symbols, next_first.as<uint32_t>());
+  run_group_first<<<(unsigned)div_up(tiles, GROUP_TILES), 256, 0, stream>>>(tile_first.as<uint32_t>(), tiles, group_first.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  run_tile_next<<<(unsigned)div_up(tiles, 256), 256, 0, stream>>>(tile_first.as<uint32_t>(), group_first.as<uint32_t>(), tiles,
+                                                                 (uint32_t)symbols, next_first.as<uint32_t>());
   BWTM_LAUNCH_CHECK();
   run_tile_resolve<<<(unsigned)div_up(tiles, 256), 256, 0, stream>>>(d_planes, (uint32_t)symbols, tiles, counts, tile_last.as<uint32_t>(),
                                                                     next_first.as<uint32_t>(), classes, ends.as<SlabEnds>());

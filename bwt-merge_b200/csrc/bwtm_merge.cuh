@@ -103,7 +103,7 @@ struct SlabEncoder
   uint64_t long_capacity;                       // long runs the transducer arrays can hold
   const uint4* slab_planes;                     // input of the last detect(), read again by emit()
   uint64_t slab_symbols;
-  DeviceBuffer tile_count, tile_first, tile_last, next_first, class_base, ends, long_len, long_shorts, tile_bytes, tile_entry,
+  DeviceBuffer tile_count, tile_first, tile_last, next_first, group_first, class_base, ends, long_len, long_shorts, tile_bytes, tile_entry,
                long_offset, checkpoints, placed, cub_temp;
   uint64_t detected_runs;                       // result of detect(): maximal runs of the slab
   uint64_t part_count, part_short, part_long;   // its parallel part, runs [1, m - 1)
