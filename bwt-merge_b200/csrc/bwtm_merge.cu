@@ -1418,7 +1418,7 @@ int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first
   uint64_t emitted = 0;
   BWTM_TRY(walk_sequences<uint64_t>(a, b, seq_first, seq_last, keys.as<uint64_t>(), capacity, &emitted, 0));
   uint64_t* sorted = nullptr;
-  BWTM_TRY(sort_keys<uint64_t>(keys.as<uint64_t>(), alt.as<uint64_t>(), emitted, 64, &sorted, 0));
+  BWTM_TRY(sort_keys<uint64_t>(keys.as<uint64_t>(), alt.as<uint64_t>(), emitted, bit_length_host(a->size), &sorted, 0));
   BWTM_CUDA(cudaMemcpy(out_sorted, sorted, emitted * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   *n_values = emitted;
   return BWTM_OK;

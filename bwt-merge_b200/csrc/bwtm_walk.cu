@@ -404,29 +404,269 @@ struct TunedSortHub
   using MaxPolicy = Policy;
 };
 
-static cudaError_t radix_sort_dispatch(void* temp, size_t& bytes, cub::DoubleBuffer<uint32_t>& keys, uint64_t n, int bits, cudaStream_t stream)
+static cudaError_t radix_sort_dispatch(void* temp, size_t& bytes, cub::DoubleBuffer<uint32_t>& keys, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream)
 {
   cub::DoubleBuffer<cub::NullType> values;
   return cub::DispatchRadixSort<false, uint32_t, cub::NullType, unsigned long long, TunedSortHub>::Dispatch(
-    temp, bytes, keys, values, (unsigned long long)n, 0, bits, true, stream);
+    temp, bytes, keys, values, (unsigned long long)n, begin_bit, end_bit, true, stream);
 }
 
-static cudaError_t radix_sort_dispatch(void* temp, size_t& bytes, cub::DoubleBuffer<uint64_t>& keys, uint64_t n, int bits, cudaStream_t stream)
+static cudaError_t radix_sort_dispatch(void* temp, size_t& bytes, cub::DoubleBuffer<uint64_t>& keys, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream)
 {
-  return cub::DeviceRadixSort::SortKeys(temp, bytes, keys, (int64_t)n, 0, bits, stream);
+  return cub::DeviceRadixSort::SortKeys(temp, bytes, keys, (int64_t)n, begin_bit, end_bit, stream);
+}
+
+template<class KeyT>
+static int radix_sort_bits(cub::DoubleBuffer<KeyT>& buffers, uint64_t n, int begin_bit, int end_bit, cudaStream_t stream)
+{
+  size_t temp_bytes = 0;
+  BWTM_CUDA(radix_sort_dispatch(nullptr, temp_bytes, buffers, n, begin_bit, end_bit, stream));
+  DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
+  BWTM_CUDA(radix_sort_dispatch(temp.ptr, temp_bytes, buffers, n, begin_bit, end_bit, stream));
+  count_launch((uint64_t)(2 + (end_bit - begin_bit + 7) / 8));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  return BWTM_OK;
+}
+
+// The low bits of the keys are not radix-sorted. RA values are spread over the positions of A about as
+// evenly as the inserted suffixes are, so after sorting by the high bits every range of 2^local_bits A
+// positions holds a moderate number of keys that only have to be COUNTED: a CTA builds the histogram of
+// its range in shared memory and writes every value as many times as it occurred. That replaces two
+// passes over the keys (of four for a 31-bit key) by one that is bound by plain streaming.
+constexpr int LOCAL_THREADS = 1024;
+
+__device__ __forceinline__ uint32_t padded(uint32_t v) { return v + (v >> 5); }   // a thread's 32 counters on 32 banks
+
+// offsets[r] = number of keys whose high part is below r, r in [0, ranges].
+template<class KeyT>
+__global__ void range_offsets(const KeyT* __restrict__ keys, uint64_t n, int local_bits, uint64_t ranges, unsigned long long* __restrict__ offsets)
+{
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(r > ranges) { return; }
+  uint64_t lo = 0, hi = n;
+  while(lo < hi)
+  {
+    uint64_t mid = lo + (hi - lo) / 2;
+    if(((uint64_t)keys[mid] >> local_bits) < r) { lo = mid + 1; } else { hi = mid; }
+  }
+  offsets[r] = lo;
+}
+
+// Ranges with more than `limit` keys (every inserted sequence contributes the value |sequences of A|, so there
+// always is one) are listed as (begin, end) pairs after the counter in heavy[0].
+constexpr int MAX_HEAVY_RANGES = 64;
+
+__global__ void range_heavy(const unsigned long long* __restrict__ offsets, uint64_t ranges, unsigned long long limit,
+                            unsigned long long* __restrict__ heavy)
+{
+  uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(r >= ranges) { return; }
+  unsigned long long begin = offsets[r], end = offsets[r + 1];
+  if(end - begin <= limit) { return; }
+  unsigned long long slot = atomicAdd(heavy, 1ull);
+  if(slot < (unsigned long long)MAX_HEAVY_RANGES) { heavy[1 + 2 * slot] = begin; heavy[2 + 2 * slot] = end; }
+}
+
+// Ranges of at most SMALL_RANGE_KEYS keys (nearly all of them): 16-bit counters, two per word, and the sorted
+// low parts are laid out in shared memory by the thread that owns the value, then stored in order.
+constexpr uint32_t SMALL_RANGE_KEYS = 65535;
+
+__device__ __forceinline__ uint32_t padded_word(uint32_t w) { return w + (w >> 4); }   // a thread's 16 words on 16 banks, odd stride
+
+template<class KeyT>
+__global__ void __launch_bounds__(LOCAL_THREADS)
+local_counting_sort_small(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned long long* __restrict__ offsets, int local_bits,
+                          unsigned long long small_keys)
+{
+  extern __shared__ uint32_t shared_words[];
+  __shared__ uint32_t warp_sums[LOCAL_THREADS / 32];
+  const uint64_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+  if(hi == lo || hi - lo > small_keys) { return; }
+  const uint32_t values = 1u << local_bits, words = values / 2, words_per_thread = words / LOCAL_THREADS;
+  uint32_t* counters = shared_words;                                                  // padded_word(words) words
+  uint16_t* staged = reinterpret_cast<uint16_t*>(shared_words + padded_word(words));  // SMALL_RANGE_KEYS + 1 entries
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t total = (uint32_t)(hi - lo);
+  for(uint32_t w = tid; w < padded_word(words); w += LOCAL_THREADS) { counters[w] = 0; }
+  __syncthreads();
+  // independent loads first, then the shared-memory atomics
+  for(uint32_t k = tid; k < total; k += 8 * LOCAL_THREADS)
+  {
+    uint32_t low[8];
+#pragma unroll
+    for(int u = 0; u < 8; u++) { low[u] = (k + u * LOCAL_THREADS < total ? (uint32_t)in[lo + k + u * LOCAL_THREADS] & (values - 1u) : 0xFFFFFFFFu); }
+#pragma unroll
+    for(int u = 0; u < 8; u++) { if(low[u] != 0xFFFFFFFFu) { atomicAdd(&counters[padded_word(low[u] >> 1)], 1u << (16 * (low[u] & 1u))); } }
+  }
+  __syncthreads();
+
+  const uint32_t first_word = tid * words_per_thread;
+  uint32_t sum = 0;
+  for(uint32_t i = 0; i < words_per_thread; i++) { uint32_t pair = counters[padded_word(first_word + i)]; sum += (pair & 0xFFFFu) + (pair >> 16); }
+  uint32_t inclusive = sum;
+#pragma unroll
+  for(int offset = 1; offset < 32; offset <<= 1)
+  {
+    uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane >= (uint32_t)offset) { inclusive += other; }
+  }
+  if(lane == 31) { warp_sums[warp] = inclusive; }
+  __syncthreads();
+  if(warp == 0)
+  {
+    uint32_t w = warp_sums[lane], scanned = w;
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+      uint32_t other = __shfl_up_sync(0xFFFFFFFFu, scanned, offset);
+      if(lane >= (uint32_t)offset) { scanned += other; }
+    }
+    warp_sums[lane] = scanned - w;
+  }
+  __syncthreads();
+  uint32_t position = warp_sums[warp] + inclusive - sum;
+  for(uint32_t i = 0; i < words_per_thread; i++)
+  {
+    uint32_t pair = counters[padded_word(first_word + i)];
+    uint32_t value = 2 * (first_word + i);
+    for(uint32_t c = pair & 0xFFFFu; c > 0; c--) { staged[position++] = (uint16_t)value; }
+    for(uint32_t c = pair >> 16; c > 0; c--) { staged[position++] = (uint16_t)(value + 1); }
+  }
+  __syncthreads();
+  const KeyT high = (KeyT)blockIdx.x << local_bits;
+  for(uint32_t o = tid; o < total; o += LOCAL_THREADS) { out[lo + o] = high | (KeyT)staged[o]; }
+}
+
+template<class KeyT>
+__global__ void __launch_bounds__(LOCAL_THREADS)
+local_counting_sort(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned long long* __restrict__ offsets, int local_bits,
+                    unsigned long long small_keys, unsigned long long limit)
+{
+  extern __shared__ uint32_t counters[];   // padded(1 << local_bits) words
+  __shared__ uint32_t warp_sums[LOCAL_THREADS / 32];
+  const uint64_t lo = offsets[blockIdx.x], hi = offsets[blockIdx.x + 1];
+  if(hi == lo || hi - lo <= small_keys || hi - lo > limit) { return; }   // small ranges: local_counting_sort_small
+  const uint32_t values = 1u << local_bits, per_thread = values / LOCAL_THREADS;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for(uint32_t v = tid; v < padded(values); v += LOCAL_THREADS) { counters[v] = 0; }
+  __syncthreads();
+  for(uint64_t k = lo + tid; k < hi; k += LOCAL_THREADS) { atomicAdd(&counters[padded((uint32_t)in[k] & (values - 1u))], 1u); }
+  __syncthreads();
+
+  // counts -> exclusive prefixes, in place: thread t owns the values [t per_thread, (t + 1) per_thread)
+  const uint32_t first = tid * per_thread;
+  uint32_t sum = 0;
+  for(uint32_t i = 0; i < per_thread; i++) { sum += counters[padded(first + i)]; }
+  uint32_t inclusive = sum;
+#pragma unroll
+  for(int offset = 1; offset < 32; offset <<= 1)
+  {
+    uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane >= (uint32_t)offset) { inclusive += other; }
+  }
+  if(lane == 31) { warp_sums[warp] = inclusive; }
+  __syncthreads();
+  if(warp == 0)
+  {
+    uint32_t w = warp_sums[lane], scanned = w;
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+      uint32_t other = __shfl_up_sync(0xFFFFFFFFu, scanned, offset);
+      if(lane >= (uint32_t)offset) { scanned += other; }
+    }
+    warp_sums[lane] = scanned - w;
+  }
+  __syncthreads();
+  uint32_t running = warp_sums[warp] + inclusive - sum;
+  for(uint32_t i = 0; i < per_thread; i++)
+  {
+    uint32_t count = counters[padded(first + i)];
+    counters[padded(first + i)] = running;
+    running += count;
+  }
+  __syncthreads();
+
+  // output position o holds the last value whose prefix is <= o
+  const KeyT high = (KeyT)blockIdx.x << local_bits;
+  const uint64_t total = hi - lo;
+  for(uint64_t o = tid; o < total; o += LOCAL_THREADS)
+  {
+    uint32_t a = 0, b = values;
+    while(b - a > 1)
+    {
+      uint32_t middle = (a + b) >> 1;
+      if((uint64_t)counters[padded(middle)] <= o) { a = middle; } else { b = middle; }
+    }
+    out[lo + o] = high | (KeyT)a;
+  }
+}
+
+static uint64_t env_number(const char* name, uint64_t fallback)
+{
+  const char* text = getenv(name);
+  return (text == nullptr ? fallback : (uint64_t)strtoull(text, nullptr, 10));
 }
 
 template<class KeyT>
 int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream)
 {
   cub::DoubleBuffer<KeyT> buffers(d_keys, d_alt);
-  size_t temp_bytes = 0;
-  BWTM_CUDA(radix_sort_dispatch(nullptr, temp_bytes, buffers, n, bits, stream));
-  DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
-  BWTM_CUDA(radix_sort_dispatch(temp.ptr, temp_bytes, buffers, n, bits, stream));
-  count_launch((uint64_t)(2 + (bits + 7) / 8));
+  // BWTM_LOCAL_SORT_MIN: smallest input that takes the counting route (tests force it with 1);
+  // BWTM_LOCAL_SORT_LIMIT: most keys one range may hold before the plain radix sort takes over.
+  const uint64_t local_min = env_number("BWTM_LOCAL_SORT_MIN", 1ull << 22);
+  const uint64_t local_limit = env_number("BWTM_LOCAL_SORT_LIMIT", 1ull << 19);
+  const uint64_t small_keys = std::min<uint64_t>(env_number("BWTM_LOCAL_SORT_SMALL", SMALL_RANGE_KEYS), SMALL_RANGE_KEYS);   // tests: 0
+  const int local_bits = std::min(15, std::max(12, bits - 16));
+  if(n < local_min || bits <= local_bits || bits - local_bits > 22)
+  {
+    BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
+    *sorted = buffers.Current();
+    return BWTM_OK;
+  }
+
+  BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, local_bits, bits, stream));
+  const uint64_t ranges = 1ull << (bits - local_bits);
+  DeviceBuffer offsets; BWTM_TRY(offsets.allocate((ranges + 1) * sizeof(unsigned long long)));
+  DeviceBuffer heavy; BWTM_TRY(heavy.allocate((1 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemsetAsync(heavy.ptr, 0, sizeof(unsigned long long), stream));
+  range_offsets<KeyT><<<(unsigned)div_up(ranges + 1, 256), 256, 0, stream>>>(buffers.Current(), n, local_bits, ranges, offsets.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  range_heavy<<<(unsigned)div_up(ranges, 256), 256, 0, stream>>>(offsets.as<unsigned long long>(), ranges, local_limit, heavy.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  const uint32_t half_words = 1u << (local_bits - 1);
+  const size_t small_bytes = (size_t)(half_words + (half_words >> 4)) * sizeof(uint32_t) + (size_t)(SMALL_RANGE_KEYS + 1) * sizeof(uint16_t);
+  BWTM_CUDA(cudaFuncSetAttribute(local_counting_sort_small<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
+  local_counting_sort_small<KeyT><<<(unsigned)ranges, LOCAL_THREADS, small_bytes, stream>>>(buffers.Current(), buffers.Alternate(),
+                                                                                           offsets.as<unsigned long long>(), local_bits, small_keys);
+  BWTM_LAUNCH_CHECK();
+  const size_t shared_bytes = (size_t)((1u << local_bits) + (1u << (local_bits - 5))) * sizeof(uint32_t);
+  BWTM_CUDA(cudaFuncSetAttribute(local_counting_sort<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
+  local_counting_sort<KeyT><<<(unsigned)ranges, LOCAL_THREADS, shared_bytes, stream>>>(buffers.Current(), buffers.Alternate(), offsets.as<unsigned long long>(),
+                                                                                       local_bits, small_keys, local_limit);
+  BWTM_LAUNCH_CHECK();
+  unsigned long long heavy_host[1 + 2 * MAX_HEAVY_RANGES];
+  BWTM_CUDA(cudaMemcpyAsync(heavy_host, heavy.ptr, sizeof(heavy_host), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  *sorted = buffers.Current();
+  if(heavy_host[0] > (unsigned long long)MAX_HEAVY_RANGES)   // the keys pile up in many ranges: plain radix sort of everything
+  {
+    BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
+    *sorted = buffers.Current();
+    return BWTM_OK;
+  }
+  // The few heavy ranges (typically long stretches of one value) get a radix sort of their low bits.
+  DeviceBuffer temp;
+  for(unsigned long long k = 0; k < heavy_host[0]; k++)
+  {
+    unsigned long long begin = heavy_host[1 + 2 * k], count = heavy_host[2 + 2 * k] - begin;
+    size_t temp_bytes = 0;
+    BWTM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, temp_bytes, buffers.Current() + begin, buffers.Alternate() + begin, (int64_t)count, 0, local_bits, stream));
+    if(temp_bytes > temp.bytes) { BWTM_TRY(temp.allocate(temp_bytes)); }
+    BWTM_CUDA(cub::DeviceRadixSort::SortKeys(temp.ptr, temp_bytes, buffers.Current() + begin, buffers.Alternate() + begin, (int64_t)count, 0, local_bits, stream));
+    count_launch((uint64_t)(2 + (local_bits + 7) / 8));
+  }
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  *sorted = buffers.Alternate();
   return BWTM_OK;
 }
 

@@ -335,3 +335,31 @@ def test_result_index_from_merged_symbols(oracle, monkeypatch, slab):
         assert all(np.array_equal(x, y) for x, y in zip(fast.LF(inside), slow.LF(inside)))
         assert np.array_equal(fast.extract(0, n), want.decode())
         assert fast.hash() == slow.hash() == want.hash()
+
+
+@pytest.mark.parametrize("wide", [False, True])
+@pytest.mark.parametrize("limit", [None, "1", "64", "1000", "wide-counters"])
+def test_counting_sort_of_low_bits(oracle, monkeypatch, wide, limit):
+    """K2 for large inputs: radix sort on the high bits, then one counting pass per range of A positions
+    (forced on small inputs here). Ranges holding more keys than the limit are radix-sorted on their own
+    (limits 64 and 1000 make some ranges heavy); more than 64 such ranges (limit 1) fall back to the plain sort."""
+    monkeypatch.setenv("BWTM_LOCAL_SORT_MIN", "1")
+    if limit == "wide-counters":      # the kernel for ranges of more than 65535 keys, on all ranges
+        monkeypatch.setenv("BWTM_LOCAL_SORT_SMALL", "0")
+    elif limit is not None:
+        monkeypatch.setenv("BWTM_LOCAL_SORT_LIMIT", limit)
+    if wide:
+        monkeypatch.setenv("BWTM_FORCE_WIDE", "1")
+    for shape in ("reads", "noisy_N", "repeats", "single"):
+        ra, bwt_a, rb, bwt_b = collections(oracle, shape)
+        A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+        DA, DB = FMI.from_rle(A.rle()), FMI.from_rle(B.rle())
+        assert np.array_equal(bwtm_b200.rank_array(DA, DB), np.sort(oracle.build_ra_walk(A, B))), shape
+        M = FMI.merge(DA, DB)
+        assert np.array_equal(M.rle(), oracle.merge(A, B).rle()), shape
+    # an A of 70000 symbols: 17-bit keys, 12 counted bits, 32 ranges
+    big_a = make_collection(oracle, 20000, 1150, 60, 0.01, 42, 5)[1]; small_b = make_collection(oracle, 20000, 300, 60, 0.02, 42, 6)[1]
+    A, B = oracle.from_comps(big_a), oracle.from_comps(small_b)
+    assert A.size > 65536
+    M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()))
+    assert np.array_equal(M.rle(), oracle.merge(A, B).rle())
