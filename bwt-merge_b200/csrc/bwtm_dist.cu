@@ -317,7 +317,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   if(local_n > 0)
   {
     BWTM_TRY(alt.allocate(local_n * sizeof(KeyT)));
-    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), local_n, bits, &sorted, stream));
+    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), local_n, bits, &sorted, stream, n_a + 1));
   }
   timings->sort_seconds = timer.stop() * 1e-3;
   phase.mark("walk + local sort");

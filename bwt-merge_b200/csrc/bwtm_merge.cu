@@ -1276,7 +1276,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
     }
     timings->ra_values = emitted;
     timer.start();
-    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream));
+    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream, a->size + 1));
     timings->sort_seconds = timer.stop() * 1e-3;
   }
   if(sorted == keys.as<KeyT>()) { alt.release(); } else { keys.release(); }
@@ -1418,7 +1418,7 @@ int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first
   uint64_t emitted = 0;
   BWTM_TRY(walk_sequences<uint64_t>(a, b, seq_first, seq_last, keys.as<uint64_t>(), capacity, &emitted, 0));
   uint64_t* sorted = nullptr;
-  BWTM_TRY(sort_keys<uint64_t>(keys.as<uint64_t>(), alt.as<uint64_t>(), emitted, bit_length_host(a->size), &sorted, 0));
+  BWTM_TRY(sort_keys<uint64_t>(keys.as<uint64_t>(), alt.as<uint64_t>(), emitted, bit_length_host(a->size), &sorted, 0, a->size + 1));
   BWTM_CUDA(cudaMemcpy(out_sorted, sorted, emitted * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   *n_values = emitted;
   return BWTM_OK;

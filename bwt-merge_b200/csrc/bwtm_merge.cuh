@@ -22,7 +22,7 @@ int walk_counters_check(const void* host_copy);   // non-zero: the output buffer
 
 // K2. Radix sort on the low `bits` bits; *sorted points into d_keys or d_alt.
 template<class KeyT>
-int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream);
+int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit = 0);   // key_limit: exclusive bound of the key values, when known
 
 // Sequential state of the byte encoder that crosses slabs (and GPU slices).
 struct EncodeControl

@@ -456,12 +456,13 @@ __global__ void range_offsets(const KeyT* __restrict__ keys, uint64_t n, int loc
 // always is one) are listed as (begin, end) pairs after the counter in heavy[0].
 constexpr int MAX_HEAVY_RANGES = 64;
 
-__global__ void range_heavy(const unsigned long long* __restrict__ offsets, uint64_t ranges, unsigned long long limit,
-                            unsigned long long* __restrict__ heavy)
+__global__ void range_heavy(const unsigned long long* __restrict__ offsets, uint64_t ranges, unsigned long long small_keys,
+                            unsigned long long limit, unsigned long long* __restrict__ heavy)
 {
   uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if(r >= ranges) { return; }
   unsigned long long begin = offsets[r], end = offsets[r + 1];
+  if(end - begin > small_keys && end - begin <= limit) { atomicAdd(heavy + 1 + 2 * MAX_HEAVY_RANGES, 1ull); }   // wide-counter ranges
   if(end - begin <= limit) { return; }
   unsigned long long slot = atomicAdd(heavy, 1ull);
   if(slot < (unsigned long long)MAX_HEAVY_RANGES) { heavy[1 + 2 * slot] = begin; heavy[2 + 2 * slot] = end; }
@@ -490,13 +491,13 @@ local_counting_sort_small(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
   for(uint32_t w = tid; w < padded_word(words); w += LOCAL_THREADS) { counters[w] = 0; }
   __syncthreads();
   // independent loads first, then the shared-memory atomics
-  for(uint32_t k = tid; k < total; k += 8 * LOCAL_THREADS)
+  for(uint32_t k = tid; k < total; k += 16 * LOCAL_THREADS)
   {
-    uint32_t low[8];
+    uint32_t low[16];
 #pragma unroll
-    for(int u = 0; u < 8; u++) { low[u] = (k + u * LOCAL_THREADS < total ? (uint32_t)in[lo + k + u * LOCAL_THREADS] & (values - 1u) : 0xFFFFFFFFu); }
+    for(int u = 0; u < 16; u++) { low[u] = (k + u * LOCAL_THREADS < total ? (uint32_t)in[lo + k + u * LOCAL_THREADS] & (values - 1u) : 0xFFFFFFFFu); }
 #pragma unroll
-    for(int u = 0; u < 8; u++) { if(low[u] != 0xFFFFFFFFu) { atomicAdd(&counters[padded_word(low[u] >> 1)], 1u << (16 * (low[u] & 1u))); } }
+    for(int u = 0; u < 16; u++) { if(low[u] != 0xFFFFFFFFu) { atomicAdd(&counters[padded_word(low[u] >> 1)], 1u << (16 * (low[u] & 1u))); } }
   }
   __syncthreads();
 
@@ -609,8 +610,9 @@ static uint64_t env_number(const char* name, uint64_t fallback)
 }
 
 template<class KeyT>
-int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream)
+int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit)
 {
+  if(key_limit == 0 || (bits < 64 && key_limit > (1ull << bits))) { key_limit = (bits < 64 ? 1ull << bits : ~0ull); }
   cub::DoubleBuffer<KeyT> buffers(d_keys, d_alt);
   // BWTM_LOCAL_SORT_MIN: smallest input that takes the counting route (tests force it with 1);
   // BWTM_LOCAL_SORT_LIMIT: most keys one range may hold before the plain radix sort takes over.
@@ -618,7 +620,11 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   const uint64_t local_limit = env_number("BWTM_LOCAL_SORT_LIMIT", 1ull << 19);
   const uint64_t small_keys = std::min<uint64_t>(env_number("BWTM_LOCAL_SORT_SMALL", SMALL_RANGE_KEYS), SMALL_RANGE_KEYS);   // tests: 0
   const int local_bits = std::min(15, std::max(12, bits - 16));
-  if(n < local_min || bits <= local_bits || bits - local_bits > 22)
+  // The counting pass costs about the same per range whatever the range holds: it pays off when the ranges
+  // are well filled (a rank of a multi-GPU merge sorts only its share of the keys over the same positions).
+  const uint64_t expected_ranges = (bits > local_bits ? std::min<uint64_t>(1ull << std::min(bits - local_bits, 40), ((key_limit - 1) >> local_bits) + 1) : 1);
+  const uint64_t local_density = env_number("BWTM_LOCAL_SORT_DENSITY", 8192);
+  if(n < local_min || bits <= local_bits || bits - local_bits > 22 || n / expected_ranges < local_density)
   {
     BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
     *sorted = buffers.Current();
@@ -626,13 +632,13 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   }
 
   BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, local_bits, bits, stream));
-  const uint64_t ranges = 1ull << (bits - local_bits);
+  const uint64_t ranges = std::min<uint64_t>(1ull << (bits - local_bits), ((key_limit - 1) >> local_bits) + 1);
   DeviceBuffer offsets; BWTM_TRY(offsets.allocate((ranges + 1) * sizeof(unsigned long long)));
-  DeviceBuffer heavy; BWTM_TRY(heavy.allocate((1 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long)));
-  BWTM_CUDA(cudaMemsetAsync(heavy.ptr, 0, sizeof(unsigned long long), stream));
+  DeviceBuffer heavy; BWTM_TRY(heavy.allocate((2 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemsetAsync(heavy.ptr, 0, (2 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long), stream));
   range_offsets<KeyT><<<(unsigned)div_up(ranges + 1, 256), 256, 0, stream>>>(buffers.Current(), n, local_bits, ranges, offsets.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
-  range_heavy<<<(unsigned)div_up(ranges, 256), 256, 0, stream>>>(offsets.as<unsigned long long>(), ranges, local_limit, heavy.as<unsigned long long>());
+  range_heavy<<<(unsigned)div_up(ranges, 256), 256, 0, stream>>>(offsets.as<unsigned long long>(), ranges, small_keys, local_limit, heavy.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
   const uint32_t half_words = 1u << (local_bits - 1);
   const size_t small_bytes = (size_t)(half_words + (half_words >> 4)) * sizeof(uint32_t) + (size_t)(SMALL_RANGE_KEYS + 1) * sizeof(uint16_t);
@@ -640,14 +646,17 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   local_counting_sort_small<KeyT><<<(unsigned)ranges, LOCAL_THREADS, small_bytes, stream>>>(buffers.Current(), buffers.Alternate(),
                                                                                            offsets.as<unsigned long long>(), local_bits, small_keys);
   BWTM_LAUNCH_CHECK();
-  const size_t shared_bytes = (size_t)((1u << local_bits) + (1u << (local_bits - 5))) * sizeof(uint32_t);
-  BWTM_CUDA(cudaFuncSetAttribute(local_counting_sort<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
-  local_counting_sort<KeyT><<<(unsigned)ranges, LOCAL_THREADS, shared_bytes, stream>>>(buffers.Current(), buffers.Alternate(), offsets.as<unsigned long long>(),
-                                                                                       local_bits, small_keys, local_limit);
-  BWTM_LAUNCH_CHECK();
-  unsigned long long heavy_host[1 + 2 * MAX_HEAVY_RANGES];
+  unsigned long long heavy_host[2 + 2 * MAX_HEAVY_RANGES];
   BWTM_CUDA(cudaMemcpyAsync(heavy_host, heavy.ptr, sizeof(heavy_host), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
+  if(heavy_host[1 + 2 * MAX_HEAVY_RANGES] > 0 && heavy_host[0] <= (unsigned long long)MAX_HEAVY_RANGES)
+  {
+    const size_t shared_bytes = (size_t)((1u << local_bits) + (1u << (local_bits - 5))) * sizeof(uint32_t);
+    BWTM_CUDA(cudaFuncSetAttribute(local_counting_sort<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shared_bytes));
+    local_counting_sort<KeyT><<<(unsigned)ranges, LOCAL_THREADS, shared_bytes, stream>>>(buffers.Current(), buffers.Alternate(), offsets.as<unsigned long long>(),
+                                                                                         local_bits, small_keys, local_limit);
+    BWTM_LAUNCH_CHECK();
+  }
   if(heavy_host[0] > (unsigned long long)MAX_HEAVY_RANGES)   // the keys pile up in many ranges: plain radix sort of everything
   {
     BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
@@ -670,7 +679,7 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   return BWTM_OK;
 }
 
-template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t);
-template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t);
+template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t, uint64_t);
+template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t, uint64_t);
 
 } // namespace bwtm
