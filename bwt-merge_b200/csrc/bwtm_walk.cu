@@ -468,11 +468,23 @@ __global__ void range_heavy(const unsigned long long* __restrict__ offsets, uint
   if(slot < (unsigned long long)MAX_HEAVY_RANGES) { heavy[1 + 2 * slot] = begin; heavy[2 + 2 * slot] = end; }
 }
 
-// Ranges of at most SMALL_RANGE_KEYS keys (nearly all of them): 16-bit counters, two per word, and the sorted
-// low parts are laid out in shared memory by the thread that owns the value, then stored in order.
+// Ranges of at most SMALL_RANGE_KEYS keys (nearly all of them): 16-bit counters, two per word. The sorted low
+// parts are laid out in shared memory without a loop over the copies of a value: the owner of a value
+// writes it (plus one) at the first output slot of the value, and at the start of every 32-slot row the
+// value reaches into; a row then is one ballot and one shuffle away from its final contents.
 constexpr uint32_t SMALL_RANGE_KEYS = 65535;
+constexpr uint32_t SMALL_RANGE_ROWS = SMALL_RANGE_KEYS / 32 + 1;
 
 __device__ __forceinline__ uint32_t padded_word(uint32_t w) { return w + (w >> 4); }   // a thread's 16 words on 16 banks, odd stride
+
+__device__ __forceinline__ void place_value(uint16_t* staged, uint16_t* row_first, uint32_t value, uint32_t count, uint32_t& position)
+{
+  if(count == 0) { return; }
+  staged[position] = (uint16_t)(value + 1);
+  const uint32_t last_row = (position + count - 1) >> 5;
+  for(uint32_t row = (position + 31) >> 5; row <= last_row; row++) { row_first[row] = (uint16_t)(value + 1); }
+  position += count;
+}
 
 template<class KeyT>
 __global__ void __launch_bounds__(LOCAL_THREADS)
@@ -485,10 +497,13 @@ local_counting_sort_small(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
   if(hi == lo || hi - lo > small_keys) { return; }
   const uint32_t values = 1u << local_bits, words = values / 2, words_per_thread = words / LOCAL_THREADS;
   uint32_t* counters = shared_words;                                                  // padded_word(words) words
-  uint16_t* staged = reinterpret_cast<uint16_t*>(shared_words + padded_word(words));  // SMALL_RANGE_KEYS + 1 entries
+  uint32_t* staged_words = shared_words + padded_word(words);
+  uint16_t* staged = reinterpret_cast<uint16_t*>(staged_words);                       // SMALL_RANGE_KEYS + 1 entries
+  uint16_t* row_first = staged + (SMALL_RANGE_KEYS + 1);                              // SMALL_RANGE_ROWS entries
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t total = (uint32_t)(hi - lo);
   for(uint32_t w = tid; w < padded_word(words); w += LOCAL_THREADS) { counters[w] = 0; }
+  for(uint32_t w = tid; w < (total + 1) / 2; w += LOCAL_THREADS) { staged_words[w] = 0; }
   __syncthreads();
   // independent loads first, then the shared-memory atomics
   for(uint32_t k = tid; k < total; k += 16 * LOCAL_THREADS)
@@ -530,12 +545,22 @@ local_counting_sort_small(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
   {
     uint32_t pair = counters[padded_word(first_word + i)];
     uint32_t value = 2 * (first_word + i);
-    for(uint32_t c = pair & 0xFFFFu; c > 0; c--) { staged[position++] = (uint16_t)value; }
-    for(uint32_t c = pair >> 16; c > 0; c--) { staged[position++] = (uint16_t)(value + 1); }
+    place_value(staged, row_first, value, pair & 0xFFFFu, position);
+    place_value(staged, row_first, value + 1, pair >> 16, position);
   }
   __syncthreads();
+
   const KeyT high = (KeyT)blockIdx.x << local_bits;
-  for(uint32_t o = tid; o < total; o += LOCAL_THREADS) { out[lo + o] = high | (KeyT)staged[o]; }
+  const uint32_t rows = (total + 31) >> 5;
+  for(uint32_t row = warp; row < rows; row += LOCAL_THREADS / 32)
+  {
+    const uint32_t o = 32 * row + lane;
+    uint32_t x = (o < total ? (uint32_t)staged[o] : 0u);
+    if(lane == 0) { x = row_first[row]; }
+    const uint32_t heads = __ballot_sync(0xFFFFFFFFu, x != 0) & ((2u << lane) - 1u);   // bit 0 is always set
+    const uint32_t mine = __shfl_sync(0xFFFFFFFFu, x, 31 - __clz(heads));
+    if(o < total) { out[lo + o] = high | (KeyT)(mine - 1u); }
+  }
 }
 
 template<class KeyT>
@@ -641,7 +666,7 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   range_heavy<<<(unsigned)div_up(ranges, 256), 256, 0, stream>>>(offsets.as<unsigned long long>(), ranges, small_keys, local_limit, heavy.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
   const uint32_t half_words = 1u << (local_bits - 1);
-  const size_t small_bytes = (size_t)(half_words + (half_words >> 4)) * sizeof(uint32_t) + (size_t)(SMALL_RANGE_KEYS + 1) * sizeof(uint16_t);
+  const size_t small_bytes = (size_t)(half_words + (half_words >> 4)) * sizeof(uint32_t) + (size_t)(SMALL_RANGE_KEYS + 1 + SMALL_RANGE_ROWS) * sizeof(uint16_t);
   BWTM_CUDA(cudaFuncSetAttribute(local_counting_sort_small<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes));
   local_counting_sort_small<KeyT><<<(unsigned)ranges, LOCAL_THREADS, small_bytes, stream>>>(buffers.Current(), buffers.Alternate(),
                                                                                            offsets.as<unsigned long long>(), local_bits, small_keys);
