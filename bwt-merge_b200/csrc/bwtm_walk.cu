@@ -482,7 +482,10 @@ __device__ __forceinline__ void place_value(uint16_t* staged, uint16_t* row_firs
   if(count == 0) { return; }
   staged[position] = (uint16_t)(value + 1);
   const uint32_t last_row = (position + count - 1) >> 5;
-  for(uint32_t row = (position + 31) >> 5; row <= last_row; row++) { row_first[row] = (uint16_t)(value + 1); }
+  uint32_t row = (position + 31) >> 5;
+  if(row <= last_row) { row_first[row] = (uint16_t)(value + 1); }   // a value of a few copies starts at most one row
+#pragma unroll 1
+  for(row++; row <= last_row; row++) { row_first[row] = (uint16_t)(value + 1); }
   position += count;
 }
 
@@ -506,13 +509,22 @@ local_counting_sort_small(const KeyT* __restrict__ in, KeyT* __restrict__ out, c
   for(uint32_t w = tid; w < (total + 1) / 2; w += LOCAL_THREADS) { staged_words[w] = 0; }
   __syncthreads();
   // independent loads first, then the shared-memory atomics
-  for(uint32_t k = tid; k < total; k += 16 * LOCAL_THREADS)
+  const KeyT* mine_in = in + lo + tid;
+  uint32_t k = tid;
+  for(; k + 7 * LOCAL_THREADS < total; k += 8 * LOCAL_THREADS, mine_in += 8 * LOCAL_THREADS)   // full batches: no bounds checks
   {
-    uint32_t low[16];
+    uint32_t low[8];
 #pragma unroll
-    for(int u = 0; u < 16; u++) { low[u] = (k + u * LOCAL_THREADS < total ? (uint32_t)in[lo + k + u * LOCAL_THREADS] & (values - 1u) : 0xFFFFFFFFu); }
+    for(int u = 0; u < 8; u++) { low[u] = (uint32_t)mine_in[u * LOCAL_THREADS] & (values - 1u); }
 #pragma unroll
-    for(int u = 0; u < 16; u++) { if(low[u] != 0xFFFFFFFFu) { atomicAdd(&counters[padded_word(low[u] >> 1)], 1u << (16 * (low[u] & 1u))); } }
+    for(int u = 0; u < 8; u++) { atomicAdd(&counters[padded_word(low[u] >> 1)], 1u << (16 * (low[u] & 1u))); }
+  }
+  {
+    uint32_t low[8];
+#pragma unroll
+    for(int u = 0; u < 8; u++) { low[u] = (k + u * LOCAL_THREADS < total ? (uint32_t)mine_in[u * LOCAL_THREADS] & (values - 1u) : 0xFFFFFFFFu); }
+#pragma unroll
+    for(int u = 0; u < 8; u++) { if(low[u] != 0xFFFFFFFFu) { atomicAdd(&counters[padded_word(low[u] >> 1)], 1u << (16 * (low[u] & 1u))); } }
   }
   __syncthreads();
 
