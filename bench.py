@@ -318,7 +318,7 @@ def main():
         stream_out = MergeParameters(); stream_out.host_output = no    # merged bytes are copied out while encoding
 
         def e2e_step():
-            a = FMI.from_rle(na); b = FMI.from_rle(nb_)
+            a, b = FMI.from_rle_pair(na, nb_)
             m = FMI.merge(a, b, stream_out)
             got = int(m.timings.merged_bytes); m.close()
             return got

@@ -25,7 +25,7 @@ ERROR_NAMES = {-1: "BWTM_ERR_ARGUMENT", -2: "BWTM_ERR_CUDA", -3: "BWTM_ERR_MEMOR
 # Every symbol include/bwtm.h declares.
 EXPORTS = [
     "bwtm_last_error", "bwtm_version", "bwtm_device_count", "bwtm_set_device", "bwtm_kernel_launches",
-    "bwtm_index_create", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_destroy", "bwtm_index_get_info",
+    "bwtm_index_create", "bwtm_index_create_pair", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_destroy", "bwtm_index_get_info",
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
     "bwtm_rank", "bwtm_lf", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
     "bwtm_shard_range", "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
@@ -94,6 +94,7 @@ def lib():
     L.bwtm_set_device.argtypes = [C.c_int]
     L.bwtm_kernel_launches.restype = C.c_uint64
     L.bwtm_index_create.argtypes = [u8p, C.c_uint64, u64p, C.POINTER(vp)]
+    L.bwtm_index_create_pair.argtypes = [u8p, C.c_uint64, u64p, u8p, C.c_uint64, u64p, C.POINTER(vp), C.POINTER(vp)]
     L.bwtm_index_create_device.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.bwtm_index_create_plain.argtypes = [u8p, C.c_uint64, C.c_uint64, C.POINTER(vp)]
     L.bwtm_index_destroy.argtypes = [vp]
@@ -191,6 +192,14 @@ class FMI:
             exp = _p(np.ascontiguousarray(expected_counts, dtype=np.uint64), u64p)
         check(lib().bwtm_index_create(_p(rle, u8p), len(rle), exp, C.byref(h)))
         return cls(h)
+
+    @classmethod
+    def from_rle_pair(cls, rle_a, rle_b):
+        """Both inputs of a merge: the second upload overlaps the first K0 (bwtm_index_create_pair)."""
+        rle_a = np.ascontiguousarray(rle_a, dtype=np.uint8); rle_b = np.ascontiguousarray(rle_b, dtype=np.uint8)
+        ha, hb = C.c_void_p(), C.c_void_p()
+        check(lib().bwtm_index_create_pair(_p(rle_a, u8p), len(rle_a), None, _p(rle_b, u8p), len(rle_b), None, C.byref(ha), C.byref(hb)))
+        return cls(ha), cls(hb)
 
     @classmethod
     def from_comps(cls, comps, slab_symbols=0):

@@ -212,15 +212,52 @@ k0_fill_planes(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t blo
     uint64_t begin = block * RLE_BLOCK;
     int limit = (int)(rle_bytes - begin < (uint64_t)RLE_BLOCK ? rle_bytes - begin : (uint64_t)RLE_BLOCK);
     uint64_t pos = starts[block];
-    decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
+    if(staged)
     {
-      if(comp != 0)
+      // The runs of a block cover consecutive positions: the bits of the current 32-position word are
+      // collected in registers. A word the thread fills from bit 0 to bit 31 belongs to it alone and is
+      // stored; the words at the two ends of its range are shared with the neighbouring threads (atomicOr).
+      uint32_t word = (uint32_t)((pos >> 5) - first_chunk), t = (uint32_t)(pos & 31u);
+      uint32_t acc0 = 0, acc1 = 0, acc2 = 0;
+      bool owned = (t == 0);
+      decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
       {
-        if(staged) { set_run_bits(planes[0], planes[1], planes[2], 1, first_chunk, comp, pos, length, true); }
-        else { set_run_bits(record_words, record_words + 1, record_words + 2, 4, 0, comp, pos, length, false); }
+        const uint32_t b0 = 0u - (comp & 1u), b1 = 0u - ((comp >> 1) & 1u), b2 = 0u - ((comp >> 2) & 1u);
+        uint64_t remaining = length;
+        while(remaining > 0)
+        {
+          uint32_t take = (uint32_t)(remaining < (uint64_t)(32u - t) ? remaining : (uint64_t)(32u - t));
+          uint32_t mask = low_mask((int)take) << t;
+          acc0 |= mask & b0; acc1 |= mask & b1; acc2 |= mask & b2;
+          t += take; remaining -= take;
+          if(t == 32u)
+          {
+            if(owned) { planes[0][word] = acc0; planes[1][word] = acc1; planes[2][word] = acc2; }
+            else
+            {
+              if(acc0 != 0) { atomicOr(&planes[0][word], acc0); }
+              if(acc1 != 0) { atomicOr(&planes[1][word], acc1); }
+              if(acc2 != 0) { atomicOr(&planes[2][word], acc2); }
+            }
+            word++; t = 0; acc0 = 0; acc1 = 0; acc2 = 0; owned = true;
+          }
+        }
+      });
+      if(t != 0)
+      {
+        if(acc0 != 0) { atomicOr(&planes[0][word], acc0); }
+        if(acc1 != 0) { atomicOr(&planes[1][word], acc1); }
+        if(acc2 != 0) { atomicOr(&planes[2][word], acc2); }
       }
-      pos += length;
-    });
+    }
+    else
+    {
+      decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
+      {
+        if(comp != 0) { set_run_bits(record_words, record_words + 1, record_words + 2, 4, 0, comp, pos, length, false); }
+        pos += length;
+      });
+    }
   }
   if(!staged) { return; }
   __syncthreads();
@@ -604,6 +641,65 @@ int bwtm_index_create(const uint8_t* rle, uint64_t rle_bytes, const uint64_t* ex
     }
   }
   *out = index;
+  return BWTM_OK;
+}
+
+static int check_counts(bwtm_index* index, const uint64_t* expected_counts)
+{
+  for(int c = 0; expected_counts != nullptr && c < SIGMA; c++)
+  {
+    if(expected_counts[c] != index->counts[c])
+    {
+      set_error("count of comp %d is %llu, expected %llu", c,
+                (unsigned long long)index->counts[c], (unsigned long long)expected_counts[c]);
+      return BWTM_ERR_ARGUMENT;
+    }
+  }
+  return BWTM_OK;
+}
+
+int bwtm_index_create_pair(const uint8_t* rle_a, uint64_t rle_bytes_a, const uint64_t* expected_counts_a,
+                           const uint8_t* rle_b, uint64_t rle_bytes_b, const uint64_t* expected_counts_b,
+                           bwtm_index** out_a, bwtm_index** out_b)
+{
+  if(rle_a == nullptr || rle_b == nullptr || out_a == nullptr || out_b == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  *out_a = nullptr; *out_b = nullptr;
+  BWTM_TRY(check_device());
+  DeviceBuffer d_a, d_b;
+  BWTM_TRY(d_a.allocate(rle_bytes_a + RLE_PADDING)); BWTM_TRY(d_b.allocate(rle_bytes_b + RLE_PADDING));
+  BWTM_CUDA(cudaMemsetAsync(d_a.as<uint8_t>() + rle_bytes_a, 0, RLE_PADDING, 0));
+  BWTM_CUDA(cudaMemsetAsync(d_b.as<uint8_t>() + rle_bytes_b, 0, RLE_PADDING, 0));
+  BWTM_CUDA(cudaStreamSynchronize(0));   // the buffers come from stream 0's pool: they are usable on the copy stream from here on
+
+  // Both uploads go to a copy stream back to back; K0 of the first input starts as soon as its bytes are
+  // there and overlaps the upload of the second one.
+  cudaStream_t copy = nullptr; cudaEvent_t arrived_a = nullptr, arrived_b = nullptr;
+  int rc = BWTM_OK;
+  bwtm_index *index_a = nullptr, *index_b = nullptr;
+  auto cleanup = [&]()
+  {
+    if(copy != nullptr) { cudaStreamSynchronize(copy); cudaStreamDestroy(copy); }
+    if(arrived_a != nullptr) { cudaEventDestroy(arrived_a); }
+    if(arrived_b != nullptr) { cudaEventDestroy(arrived_b); }
+  };
+  auto failed = [&](const char* what) { set_error("%s: %s", what, cudaGetErrorString(cudaGetLastError())); cleanup(); return BWTM_ERR_CUDA; };
+  if(cudaStreamCreateWithFlags(&copy, cudaStreamNonBlocking) != cudaSuccess) { return failed("cannot create the copy stream"); }
+  if(cudaEventCreateWithFlags(&arrived_a, cudaEventDisableTiming) != cudaSuccess ||
+     cudaEventCreateWithFlags(&arrived_b, cudaEventDisableTiming) != cudaSuccess) { return failed("cannot create events"); }
+  if(cudaMemcpyAsync(d_a.ptr, rle_a, rle_bytes_a, cudaMemcpyHostToDevice, copy) != cudaSuccess || cudaEventRecord(arrived_a, copy) != cudaSuccess ||
+     cudaMemcpyAsync(d_b.ptr, rle_b, rle_bytes_b, cudaMemcpyHostToDevice, copy) != cudaSuccess || cudaEventRecord(arrived_b, copy) != cudaSuccess)
+  {
+    return failed("cannot upload the run-length bytes");
+  }
+  if(cudaStreamWaitEvent(0, arrived_a, 0) != cudaSuccess) { return failed("cannot order the streams"); }
+  rc = index_from_device_rle(d_a.as<uint8_t>(), rle_bytes_a, 0, &index_a);
+  if(rc == BWTM_OK) { d_a.detach(); rc = check_counts(index_a, expected_counts_a); }
+  if(rc == BWTM_OK && cudaStreamWaitEvent(0, arrived_b, 0) != cudaSuccess) { set_error("cannot order the streams"); rc = BWTM_ERR_CUDA; }
+  if(rc == BWTM_OK) { rc = index_from_device_rle(d_b.as<uint8_t>(), rle_bytes_b, 0, &index_b); }
+  if(rc == BWTM_OK) { d_b.detach(); rc = check_counts(index_b, expected_counts_b); }
+  cleanup();
+  if(rc != BWTM_OK) { index_free(index_a); index_free(index_b); return rc; }
+  *out_a = index_a; *out_b = index_b;
   return BWTM_OK;
 }
 

@@ -121,6 +121,12 @@ uint64_t bwtm_kernel_launches(void);
    If `expected_counts` is not NULL (6 values) the decoded per-comp counts must match it. */
 int bwtm_index_create(const uint8_t* rle, uint64_t rle_bytes, const uint64_t* expected_counts,
                       bwtm_index** out);
+/* Both inputs of a merge at once, the way FMI::FMI(FMI& a, FMI& b, ...) receives them (fmi.cpp:336): the upload
+   of the second one runs while the rank structure of the first one is built. Same results as two calls of
+   bwtm_index_create; on failure neither index is returned. */
+int bwtm_index_create_pair(const uint8_t* rle_a, uint64_t rle_bytes_a, const uint64_t* expected_counts_a,
+                           const uint8_t* rle_b, uint64_t rle_bytes_b, const uint64_t* expected_counts_b,
+                           bwtm_index** out_a, bwtm_index** out_b);
 /* Same, from RLE bytes that already live in device memory (copied). */
 int bwtm_index_create_device(const void* rle_device, uint64_t rle_bytes, bwtm_index** out);
 /* From a plain symbol sequence (one comp value per byte): the device counterpart of PlainData::read

@@ -363,3 +363,16 @@ def test_counting_sort_of_low_bits(oracle, monkeypatch, wide, limit):
     assert A.size > 65536
     M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()))
     assert np.array_equal(M.rle(), oracle.merge(A, B).rle())
+
+
+def test_create_pair(oracle):
+    """bwtm_index_create_pair = two bwtm_index_create calls (the second upload overlaps the first K0)."""
+    ra, bwt_a, rb, bwt_b = collections(oracle, "reads")
+    A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+    DA, DB = FMI.from_rle_pair(A.rle(), B.rle())
+    for D, O in ((DA, A), (DB, B)):
+        assert D.size() == O.size and D.sequences() == O.sequences and np.array_equal(D.counts(), O.counts())
+        assert np.array_equal(D.rle(), O.rle()) and np.array_equal(D.extract(), O.decode()) and D.hash() == O.hash()
+    assert np.array_equal(FMI.merge(DA, DB).rle(), oracle.merge(A, B).rle())
+    with pytest.raises(bwtm_b200.BwtmError):
+        FMI.from_rle_pair(A.rle(), np.zeros(0, dtype=np.uint8))
