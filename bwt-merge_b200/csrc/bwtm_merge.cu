@@ -398,8 +398,23 @@ copy_to_host(uint8_t* __restrict__ host, const uint8_t* __restrict__ device, uin
   uint64_t vectors = (bytes - head) / 16;
   const uint4* src = reinterpret_cast<const uint4*>(device + head);
   uint4* dst = reinterpret_cast<uint4*>(host + head);
-  for(uint64_t i = tid; i < vectors; i += threads) { dst[i] = src[i]; }
+  // Few CTAs, four independent 16-byte copies per thread and round: enough bytes in flight for the PCIe link
+  // without taking many SMs away from the encoder kernels running beside this one.
+  uint64_t i = tid;
+  for(; i + 3 * threads < vectors; i += 4 * threads)
+  {
+    uint4 v0 = src[i], v1 = src[i + threads], v2 = src[i + 2 * threads], v3 = src[i + 3 * threads];
+    dst[i] = v0; dst[i + threads] = v1; dst[i + 2 * threads] = v2; dst[i + 3 * threads] = v3;
+  }
+  for(; i < vectors; i += threads) { dst[i] = src[i]; }
   for(uint64_t i = head + vectors * 16 + tid; i < bytes; i += threads) { host[i] = device[i]; }
+}
+
+static unsigned copy_ctas()
+{
+  const char* text = getenv("BWTM_COPY_CTAS");
+  int n = (text == nullptr ? 8 : atoi(text));
+  return (unsigned)(n < 1 ? 1 : n);
 }
 
 int flush_to_host(OutputBuffer* out, const EncodeControl* d_control, cudaStream_t stream)
@@ -421,7 +436,7 @@ int flush_to_host(OutputBuffer* out, const EncodeControl* d_control, cudaStream_
   BWTM_CUDA(cudaStreamWaitEvent(sink->stream, sink->ready, 0));
   if(sink->device_visible)
   {
-    copy_to_host<<<64, 256, 0, sink->stream>>>(sink->ptr + sink->copied, out->ptr + sink->copied, final_bytes - sink->copied);
+    copy_to_host<<<copy_ctas(), 256, 0, sink->stream>>>(sink->ptr + sink->copied, out->ptr + sink->copied, final_bytes - sink->copied);
     BWTM_LAUNCH_CHECK();
   }
   else

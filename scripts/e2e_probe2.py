@@ -15,7 +15,7 @@ for it in range(5):
     t0 = sync(); dev.copy_(ra, non_blocking=True); t1 = sync()
     a = FMI.from_rle(ra.numpy()); t2 = sync()
     b = FMI.from_rle(rb.numpy()); t3 = sync()
-    p = MergeParameters(); p.host_output = out
+    p = MergeParameters(); p.host_output = out; p.slab_symbols = int(__import__("os").environ.get("SLAB", "0"))
     m = FMI.merge(a, b, p); t4 = sync()
     t = m.timings
     print("it %d: raw H2D %.2f ms (%.1f GB/s)  create A %.2f  create B %.2f  merge %.2f (api total %.2f: search %.1f sort %.1f il %.1f enc %.1f idx %.1f)  step %.2f" %
