@@ -273,26 +273,27 @@ __global__ void __launch_bounds__(64)
 enc_tile_maps(const uint32_t* __restrict__ long_len, const uint32_t* __restrict__ long_shorts, uint64_t n_long,
               uint32_t* __restrict__ tile_bytes, uint16_t* __restrict__ checkpoints)
 {
-  __shared__ uint32_t s_len[LONG_SUB], s_nat[LONG_SUB], s_before[LONG_SUB];
-  uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
-  uint64_t last = (first + LONG_TILE < n_long ? first + LONG_TILE : n_long);
-  uint32_t p = threadIdx.x;
-  for(uint64_t chunk = first; chunk < last; chunk += LONG_SUB)
+  // The whole tile is staged first (coalesced, all loads in flight at once): the dependent chain below then
+  // only touches shared memory. A long run is packed as length (upper bits) and the residue of its `before`.
+  __shared__ uint32_t s_len[LONG_TILE];
+  __shared__ uint8_t  s_before[LONG_TILE], s_nat[LONG_TILE];
+  const uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
+  const uint32_t count = (uint32_t)(first + LONG_TILE < n_long ? LONG_TILE : n_long - first);
+  for(uint32_t k = threadIdx.x; k < count; k += 64)
   {
-    uint64_t sub = chunk / LONG_SUB;
-    checkpoints[sub * 64 + threadIdx.x] = (uint16_t)(p - threadIdx.x);
-    __syncthreads();
-    if(threadIdx.x < LONG_SUB && chunk + threadIdx.x < last)
+    uint32_t length = long_len[first + k];
+    s_len[k] = length; s_nat[k] = (uint8_t)natural_bytes(length);
+    s_before[k] = (uint8_t)(long_shorts[first + k] & 63u);
+  }
+  __syncthreads();
+  uint32_t p = threadIdx.x;
+  for(uint32_t chunk = 0; chunk < count; chunk += LONG_SUB)
+  {
+    checkpoints[((first + chunk) / LONG_SUB) * 64 + threadIdx.x] = (uint16_t)(p - threadIdx.x);
+    const uint32_t end = (chunk + LONG_SUB < count ? chunk + LONG_SUB : count);
+    for(uint32_t k = chunk; k < end; k++)
     {
-      uint32_t length = long_len[chunk + threadIdx.x];
-      s_len[threadIdx.x] = length; s_nat[threadIdx.x] = natural_bytes(length);
-      s_before[threadIdx.x] = long_shorts[chunk + threadIdx.x];
-    }
-    __syncthreads();
-    int count = (int)(last - chunk < (uint64_t)LONG_SUB ? last - chunk : (uint64_t)LONG_SUB);
-    for(int k = 0; k < count; k++)
-    {
-      uint32_t state = (s_before[k] + p) & 63u;
+      uint32_t state = ((uint32_t)s_before[k] + p) & 63u;
       p += long_run_bytes_fast(s_len[k], s_nat[k], state);
     }
   }
@@ -305,7 +306,7 @@ __global__ void __launch_bounds__(256)
 enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint64_t tiles,
               unsigned long long n_short, unsigned long long n_long, unsigned long long* __restrict__ tile_entry)
 {
-  __shared__ uint32_t staged[SCAN_CHUNK * 64];
+  __shared__ __align__(16) uint32_t staged[SCAN_CHUNK * 64];
   __shared__ unsigned long long entries[SCAN_CHUNK];
   __shared__ unsigned long long carried;
   const uint32_t base = (uint32_t)(ctl->slab_base & 63u);
@@ -314,7 +315,21 @@ enc_tile_scan(EncodeControl* ctl, const uint32_t* __restrict__ tile_bytes, uint6
   for(uint64_t first = 0; first < tiles; first += SCAN_CHUNK)
   {
     uint64_t count = (tiles - first < (uint64_t)SCAN_CHUNK ? tiles - first : (uint64_t)SCAN_CHUNK);
-    for(uint64_t k = threadIdx.x; k < count * 64; k += blockDim.x) { staged[k] = tile_bytes[first * 64 + k]; }
+    {
+      // 16-byte loads, all of a thread's loads issued before the first store
+      const uint4* source = reinterpret_cast<const uint4*>(tile_bytes + first * 64);
+      uint4* target = reinterpret_cast<uint4*>(staged);
+      constexpr int ROUNDS = SCAN_CHUNK * 16 / 256;
+      uint4 held[ROUNDS];
+#pragma unroll
+      for(int round = 0; round < ROUNDS; round++)
+      {
+        uint64_t k = (uint64_t)round * 256 + threadIdx.x;
+        held[round] = (k < count * 16 ? source[k] : make_uint4(0, 0, 0, 0));
+      }
+#pragma unroll
+      for(int round = 0; round < ROUNDS; round++) { target[round * 256 + threadIdx.x] = held[round]; }
+    }
     __syncthreads();
     if(threadIdx.x == 0)
     {
