@@ -169,7 +169,7 @@ k0_block_lengths(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t b
 constexpr int K0_PLANE_WORDS = 3072;   // 32-position chunks per CTA range held in shared memory
 
 __device__ __forceinline__ void set_run_bits(uint32_t* p0, uint32_t* p1, uint32_t* p2, uint64_t stride,
-                                             uint64_t first_chunk, uint32_t comp, uint64_t pos, uint64_t length, bool shared)
+                                             uint64_t first_chunk, uint32_t comp, uint64_t pos, uint64_t length)
 {
   uint64_t p = pos, remaining = length;
   while(remaining > 0)
@@ -183,7 +183,6 @@ __device__ __forceinline__ void set_run_bits(uint32_t* p0, uint32_t* p1, uint32_
     if(comp & 4u) { atomicOr(p2 + index, mask); }
     p += take; remaining -= take;
   }
-  (void)shared;
 }
 
 __global__ void __launch_bounds__(K0_THREADS)
@@ -254,7 +253,7 @@ k0_fill_planes(const uint8_t* __restrict__ rle, uint64_t rle_bytes, uint64_t blo
     {
       decode_staged_block(smem + threadIdx.x * K0_STRIDE, limit, [&](uint32_t comp, uint64_t length)
       {
-        if(comp != 0) { set_run_bits(record_words, record_words + 1, record_words + 2, 4, 0, comp, pos, length, false); }
+        if(comp != 0) { set_run_bits(record_words, record_words + 1, record_words + 2, 4, 0, comp, pos, length); }
         pos += length;
       });
     }
