@@ -274,16 +274,17 @@ enc_tile_maps(const uint32_t* __restrict__ long_len, const uint32_t* __restrict_
               uint32_t* __restrict__ tile_bytes, uint16_t* __restrict__ checkpoints)
 {
   // The whole tile is staged first (coalesced, all loads in flight at once): the dependent chain below then
-  // only touches shared memory. A long run is packed as length (upper bits) and the residue of its `before`.
+  // only touches shared memory. Per run one byte: bits 0-5 the residue of its `before`, bit 6 "two-byte run"
+  // (length 42..169, nearly all long runs), bit 7 "length >= 83" (what the closed form needs to know).
   __shared__ uint32_t s_len[LONG_TILE];
-  __shared__ uint8_t  s_before[LONG_TILE], s_nat[LONG_TILE];
+  __shared__ uint8_t  s_entry[LONG_TILE];
   const uint64_t first = (uint64_t)blockIdx.x * LONG_TILE;
   const uint32_t count = (uint32_t)(first + LONG_TILE < n_long ? LONG_TILE : n_long - first);
   for(uint32_t k = threadIdx.x; k < count; k += 64)
   {
     uint32_t length = long_len[first + k];
-    s_len[k] = length; s_nat[k] = (uint8_t)natural_bytes(length);
-    s_before[k] = (uint8_t)(long_shorts[first + k] & 63u);
+    s_len[k] = length;
+    s_entry[k] = (uint8_t)((long_shorts[first + k] & 63u) | (natural_bytes(length) == 2u ? 64u : 0u) | (length >= 2u * MAX_RUN - 1u ? 128u : 0u));
   }
   __syncthreads();
   uint32_t p = threadIdx.x;
@@ -293,8 +294,10 @@ enc_tile_maps(const uint32_t* __restrict__ long_len, const uint32_t* __restrict_
     const uint32_t end = (chunk + LONG_SUB < count ? chunk + LONG_SUB : count);
     for(uint32_t k = chunk; k < end; k++)
     {
-      uint32_t state = ((uint32_t)s_before[k] + p) & 63u;
-      p += long_run_bytes_fast(s_len[k], s_nat[k], state);
+      const uint32_t entry = s_entry[k];
+      const uint32_t state = (entry + p) & 63u;
+      if(entry & 64u) { p += 2u + ((state == 63u) ? (entry >> 7) : 0u); }     // same for all threads of the block
+      else { uint32_t length = s_len[k]; p += long_run_bytes_fast(length, natural_bytes(length), state); }
     }
   }
   tile_bytes[(uint64_t)blockIdx.x * 64 + threadIdx.x] = p - threadIdx.x;
