@@ -259,6 +259,9 @@ def main():
         AB = FMI.synthetic(args.genome, args.genome_seed, args.read_len, thr, [(args.seed_a, args.reads), (args.seed_b, args.reads)])
         reference_bytes = AB.rle(); AB.close()
 
+    # The stream-ordered allocator pool settles after a few identical steps (a first step can cost 50+ ms more):
+    # never fewer than three warm-up merges, whatever was asked for.
+    args.warmup = max(3, args.warmup)
     for _ in range(args.warmup):
         M = one_merge()
         if reference_bytes is not None:
