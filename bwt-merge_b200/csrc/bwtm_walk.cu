@@ -661,8 +661,9 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   // are well filled (a rank of a multi-GPU merge sorts only its share of the keys over the same positions).
   const uint64_t expected_ranges = (bits > local_bits ? std::min<uint64_t>(1ull << std::min(bits - local_bits, 40), ((key_limit - 1) >> local_bits) + 1) : 1);
   const uint64_t local_density = env_number("BWTM_LOCAL_SORT_DENSITY", 8192);
+  const uint64_t max_density = env_number("BWTM_LOCAL_SORT_MAX_DENSITY", 1ull << 19);   // 0: no upper bound (tests)
   if(n < local_min || bits <= local_bits || bits - local_bits > 22 || n / expected_ranges < local_density ||
-     n / expected_ranges > local_limit)   // nearly every range would be a heavy one (a small A under a large B)
+     (max_density > 0 && n / expected_ranges > max_density))   // nearly every range would be a heavy one (a small A under a large B)
   {
     BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
     *sorted = buffers.Current();

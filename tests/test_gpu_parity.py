@@ -344,6 +344,7 @@ def test_counting_sort_of_low_bits(oracle, monkeypatch, wide, limit):
     (forced on small inputs here). Ranges holding more keys than the limit are radix-sorted on their own
     (limits 64 and 1000 make some ranges heavy); more than 64 such ranges (limit 1) fall back to the plain sort."""
     monkeypatch.setenv("BWTM_LOCAL_SORT_MIN", "1"); monkeypatch.setenv("BWTM_LOCAL_SORT_DENSITY", "0")
+    monkeypatch.setenv("BWTM_LOCAL_SORT_MAX_DENSITY", "0")
     if limit == "wide-counters":      # the kernel for ranges of more than 65535 keys, on all ranges
         monkeypatch.setenv("BWTM_LOCAL_SORT_SMALL", "0")
     elif limit is not None:
