@@ -336,6 +336,31 @@ def main():
         e2e = {"value": n_b / e2e_s, "unit": "bases/s", "h2d_bytes_per_step": int(len(na) + len(nb_)),
                "d2h_bytes_per_step": int(got), "ms_per_step": e2e_s * 1e3, "steps_ms": [round(x, 2) for x in step_ms]}
 
+    if not args.no_e2e and world > 1 and os.environ.get("BWTM_BENCH_NO_DIST_E2E") is None:
+        # N GPUs: every rank uploads its replica of both inputs from pinned host memory and builds K0, the merge is the
+        # distributed one, rank 0 reads the merged bytes back. Wall clock between barriers, max over ranks.
+        rle_a = torch.from_numpy(A.rle()).pin_memory(); rle_b = torch.from_numpy(B.rle()).pin_memory()
+        out = torch.empty(merged_bytes + 4096, dtype=torch.uint8).pin_memory()
+        na, nb_, no = rle_a.numpy(), rle_b.numpy(), out.numpy()
+
+        def e2e_step_dist():
+            a, b = FMI.from_rle_pair(na, nb_)
+            m = comm.merge(a, b, params)
+            got = int(m.download_into(no)) if rank == 0 else int(m.bytes())
+            m.close()
+            return got
+        for _ in range(max(3, args.warmup)):
+            e2e_step_dist()
+        step_ms = []
+        for _ in range(max(1, args.steps)):
+            barrier(); t0 = time.perf_counter()
+            got = e2e_step_dist()
+            barrier(); elapsed = torch.tensor([(time.perf_counter() - t0) * 1e3], device="cuda")
+            dist.all_reduce(elapsed, op=dist.ReduceOp.MAX); step_ms.append(float(elapsed.item()))
+        e2e_s = float(np.mean(step_ms)) * 1e-3
+        e2e = {"value": n_b / e2e_s, "unit": "bases/s", "h2d_bytes_per_step": int(world * (len(na) + len(nb_))),
+               "d2h_bytes_per_step": int(got), "ms_per_step": e2e_s * 1e3, "steps_ms": [round(x, 2) for x in step_ms]}
+
     if rank != 0:
         return 0
 
