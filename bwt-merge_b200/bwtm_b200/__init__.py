@@ -25,7 +25,7 @@ ERROR_NAMES = {-1: "BWTM_ERR_ARGUMENT", -2: "BWTM_ERR_CUDA", -3: "BWTM_ERR_MEMOR
 # Every symbol include/bwtm.h declares.
 EXPORTS = [
     "bwtm_last_error", "bwtm_version", "bwtm_device_count", "bwtm_set_device", "bwtm_kernel_launches",
-    "bwtm_index_create", "bwtm_index_create_pair", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_destroy", "bwtm_index_get_info",
+    "bwtm_index_create", "bwtm_index_create_pair", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_create_runs", "bwtm_index_destroy", "bwtm_index_get_info",
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
     "bwtm_rank", "bwtm_lf", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
     "bwtm_shard_range", "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
@@ -97,6 +97,7 @@ def lib():
     L.bwtm_index_create_pair.argtypes = [u8p, C.c_uint64, u64p, u8p, C.c_uint64, u64p, C.POINTER(vp), C.POINTER(vp)]
     L.bwtm_index_create_device.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
     L.bwtm_index_create_plain.argtypes = [u8p, C.c_uint64, C.c_uint64, C.POINTER(vp)]
+    L.bwtm_index_create_runs.argtypes = [u8p, C.c_uint64, C.c_int, C.c_uint64, C.POINTER(vp)]
     L.bwtm_index_destroy.argtypes = [vp]
     L.bwtm_index_get_info.argtypes = [vp, C.POINTER(IndexInfo)]
     L.bwtm_index_download.argtypes = [vp, u8p, C.c_uint64, u64p]
@@ -191,6 +192,16 @@ class FMI:
         if expected_counts is not None:
             exp = _p(np.ascontiguousarray(expected_counts, dtype=np.uint64), u64p)
         check(lib().bwtm_index_create(_p(rle, u8p), len(rle), exp, C.byref(h)))
+        return cls(h)
+
+    RUNS_ROPEBWT, RUNS_SGA = 0, 1
+
+    @classmethod
+    def from_run_bytes(cls, runs, layout, slab_symbols=0):
+        """From one run per byte (RopeData::read / SGAData::read, formats.cpp:286-310, 403-429), decoded on the device."""
+        runs = np.ascontiguousarray(runs, dtype=np.uint8)
+        h = C.c_void_p()
+        check(lib().bwtm_index_create_runs(_p(runs, u8p), len(runs), layout, slab_symbols, C.byref(h)))
         return cls(h)
 
     @classmethod

@@ -1087,26 +1087,19 @@ int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, 
   return BWTM_OK;
 }
 
-int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out)
+// Records whose plane chunks hold a complete sequence of n symbols -> run-length bytes (K3 + K5, slab by slab)
+// -> index. Takes the records over on success.
+static int index_from_filled_records(DeviceBuffer& records, uint64_t n, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out)
 {
-  if(n == 0) { set_error("empty sequence"); return BWTM_ERR_ARGUMENT; }
   uint64_t slab = clamp_slab(slab_symbols, n);
   SlabEncoder encoder; BWTM_TRY(encoder.init(slab, stream));
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
   OutputBuffer buffer = { nullptr, 0, 0, nullptr };
   int rc = ensure_capacity(&buffer, n / 4 + (1 << 20), 0, stream);
-  // Symbols -> plane chunks of the records (the layout the encoder reads), slab by slab.
-  if((reinterpret_cast<uintptr_t>(d_symbols) & 15) != 0) { set_error("symbol array is not 16-byte aligned"); device_free(buffer.ptr); return BWTM_ERR_INTERNAL; }
-  DeviceBuffer records;
-  uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
-  BWTM_TRY(records.allocate(record_bytes));
-  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
   for(uint64_t p0 = 0; rc == BWTM_OK && p0 < n; p0 += slab)
   {
-    uint64_t count = std::min(slab, n - p0);
-    rc = planes_from_symbols(d_symbols + p0, p0, count, records.as<uint4>(), stream);
-    if(rc == BWTM_OK) { rc = encoder.encode(records.as<uint4>() + (p0 >> 5), count, &buffer, control.as<EncodeControl>(), stream); }
+    rc = encoder.encode(records.as<uint4>() + (p0 >> 5), std::min(slab, n - p0), &buffer, control.as<EncodeControl>(), stream);
   }
   if(rc == BWTM_OK) { rc = encoder.finish(&buffer, control.as<EncodeControl>(), stream); }
   EncodeControl ctl;
@@ -1117,6 +1110,140 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   if(rc == BWTM_OK) { rc = finish_index(&buffer, ctl.out_size, nullptr, 0, false, stream, out, &records, n); }
   device_free(buffer.ptr);
   return rc;
+}
+
+int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out)
+{
+  if(n == 0) { set_error("empty sequence"); return BWTM_ERR_ARGUMENT; }
+  // Symbols -> plane chunks of the records (the layout the encoder reads).
+  if((reinterpret_cast<uintptr_t>(d_symbols) & 15) != 0) { set_error("symbol array is not 16-byte aligned"); return BWTM_ERR_INTERNAL; }
+  DeviceBuffer records;
+  uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
+  BWTM_TRY(records.allocate(record_bytes));
+  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
+  BWTM_TRY(planes_from_symbols(d_symbols, 0, n, records.as<uint4>(), stream));
+  return index_from_filled_records(records, n, slab_symbols, stream, out);
+}
+
+// One run per byte (RopeBWT: length << 3 | comp; SGA: comp << 5 | length; lengths 1..31): the device counterpart
+// of RopeData::read (formats.cpp:286-310) and SGAData::read (formats.cpp:403-429). Positions of the runs come
+// from a two-level prefix sum of the lengths, every run sets its bits in the plane chunks, and K3 finds the
+// MAXIMAL runs there, which is what the reference's RunBuffer makes of consecutive runs of one symbol.
+constexpr int RUN_BYTES_PER_BLOCK = 1024;
+
+__device__ __forceinline__ void decode_run_byte(uint32_t byte, int layout, uint32_t& comp, uint32_t& length)
+{
+  if(layout == BWTM_RUNS_SGA) { comp = byte >> 5; length = byte & 0x1Fu; }
+  else { comp = byte & 7u; length = byte >> 3; }
+}
+
+__global__ void __launch_bounds__(256)
+run_bytes_survey(const uint8_t* __restrict__ runs, uint64_t n_runs, int layout, unsigned long long* __restrict__ block_sums,
+                 unsigned long long* __restrict__ invalid)
+{
+  __shared__ uint32_t warp_sums[8];
+  uint32_t sum = 0, bad = 0;
+  for(int k = 0; k < RUN_BYTES_PER_BLOCK / 256; k++)
+  {
+    uint64_t i = (uint64_t)blockIdx.x * RUN_BYTES_PER_BLOCK + k * 256 + threadIdx.x;
+    if(i < n_runs)
+    {
+      uint32_t comp, length; decode_run_byte(runs[i], layout, comp, length);
+      sum += length; bad += (length == 0 || comp >= (uint32_t)SIGMA ? 1u : 0u);
+    }
+  }
+  if(bad != 0) { atomicAdd(invalid, (unsigned long long)bad); }
+#pragma unroll
+  for(int offset = 16; offset > 0; offset >>= 1) { sum += __shfl_down_sync(0xFFFFFFFFu, sum, offset); }
+  if((threadIdx.x & 31) == 0) { warp_sums[threadIdx.x >> 5] = sum; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    uint32_t total = 0;
+    for(int w = 0; w < 8; w++) { total += warp_sums[w]; }
+    block_sums[blockIdx.x] = total;
+  }
+}
+
+// Thread t of a block takes the bytes 4t .. 4t+3 of the block's 1024: positions by a block scan of the sums.
+__global__ void __launch_bounds__(256)
+run_bytes_fill(const uint8_t* __restrict__ runs, uint64_t n_runs, int layout, const unsigned long long* __restrict__ block_start,
+               uint32_t* __restrict__ record_words)
+{
+  __shared__ uint32_t warp_sums[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint32_t comp[4], length[4], sum = 0;
+#pragma unroll
+  for(int k = 0; k < 4; k++)
+  {
+    uint64_t i = (uint64_t)blockIdx.x * RUN_BYTES_PER_BLOCK + 4 * threadIdx.x + k;
+    comp[k] = 0; length[k] = 0;
+    if(i < n_runs) { decode_run_byte(runs[i], layout, comp[k], length[k]); }
+    sum += length[k];
+  }
+  uint32_t inclusive = sum;
+#pragma unroll
+  for(int offset = 1; offset < 32; offset <<= 1)
+  {
+    uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane >= offset) { inclusive += other; }
+  }
+  if(lane == 31) { warp_sums[warp] = inclusive; }
+  __syncthreads();
+  uint64_t position = block_start[blockIdx.x] + inclusive - sum;
+  for(int w = 0; w < warp; w++) { position += warp_sums[w]; }
+#pragma unroll
+  for(int k = 0; k < 4; k++)
+  {
+    uint64_t p = position; uint32_t remaining = length[k];
+    position += length[k];
+    if(comp[k] == 0) { continue; }
+    while(remaining > 0)   // at most two words: a run has at most 31 symbols
+    {
+      uint32_t t = (uint32_t)(p & 31u);
+      uint32_t take = (remaining < 32u - t ? remaining : 32u - t);
+      uint32_t mask = low_mask((int)take) << t;
+      uint32_t* chunk = record_words + (p >> 5) * 4;
+      if(comp[k] & 1u) { atomicOr(chunk + 0, mask); }
+      if(comp[k] & 2u) { atomicOr(chunk + 1, mask); }
+      if(comp[k] & 4u) { atomicOr(chunk + 2, mask); }
+      p += take; remaining -= take;
+    }
+  }
+}
+
+int index_from_run_bytes(const uint8_t* d_runs, uint64_t n_runs, int layout, uint64_t slab_symbols, cudaStream_t stream, bwtm_index** out)
+{
+  if(n_runs == 0) { set_error("empty sequence"); return BWTM_ERR_ARGUMENT; }
+  if(layout != BWTM_RUNS_ROPEBWT && layout != BWTM_RUNS_SGA) { set_error("unknown run byte layout %d", layout); return BWTM_ERR_ARGUMENT; }
+  const uint64_t blocks = div_up(n_runs, RUN_BYTES_PER_BLOCK);
+  DeviceBuffer sums; BWTM_TRY(sums.allocate((blocks + 2) * sizeof(unsigned long long)));
+  unsigned long long* block_start = sums.as<unsigned long long>();
+  unsigned long long* invalid = block_start + blocks + 1;
+  BWTM_CUDA(cudaMemsetAsync(block_start + blocks, 0, 2 * sizeof(unsigned long long), stream));
+  run_bytes_survey<<<(unsigned)blocks, 256, 0, stream>>>(d_runs, n_runs, layout, block_start, invalid);
+  BWTM_LAUNCH_CHECK();
+  size_t temp_bytes = 0;
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, temp_bytes, block_start, block_start, (int64_t)(blocks + 1), stream));
+  DeviceBuffer temp; BWTM_TRY(temp.allocate(temp_bytes));
+  BWTM_CUDA(cub::DeviceScan::ExclusiveSum(temp.ptr, temp_bytes, block_start, block_start, (int64_t)(blocks + 1), stream));
+  count_launch(2);
+  unsigned long long tail[2] = { 0, 0 };   // total symbols, invalid bytes
+  BWTM_CUDA(cudaMemcpyAsync(tail, block_start + blocks, sizeof(tail), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  if(tail[1] != 0)
+  {
+    set_error("%llu run bytes have length 0 or a comp value above %d", tail[1], SIGMA - 1);
+    return BWTM_ERR_ALPHABET;
+  }
+  const uint64_t n = tail[0];
+  DeviceBuffer records;
+  uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
+  BWTM_TRY(records.allocate(record_bytes));
+  BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
+  run_bytes_fill<<<(unsigned)blocks, 256, 0, stream>>>(d_runs, n_runs, layout, block_start, records.as<uint32_t>());
+  BWTM_LAUNCH_CHECK();
+  return index_from_filled_records(records, n, slab_symbols, stream, out);
 }
 
 // K1 and K2 overlapped. The walk is bound by random line requests and leaves most of the HBM bandwidth
@@ -1424,6 +1551,21 @@ int bwtm_merge(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options, 
   if(!keep) { index_free(a); index_free(b); }
   if(timings != nullptr) { *timings = local; }
   return rc;
+}
+
+int bwtm_index_create_runs(const uint8_t* runs, uint64_t n_runs, int layout, uint64_t slab_symbols, bwtm_index** out)
+{
+  if(runs == nullptr || out == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  *out = nullptr;
+  int count = 0;
+  if(cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+  {
+    cudaGetLastError(); set_error("no CUDA device available; this library has no CPU fallback"); return BWTM_ERR_CUDA;
+  }
+  if(n_runs == 0) { set_error("empty sequence"); return BWTM_ERR_ARGUMENT; }
+  DeviceBuffer d_runs; BWTM_TRY(d_runs.allocate(n_runs));
+  BWTM_CUDA(cudaMemcpy(d_runs.ptr, runs, n_runs, cudaMemcpyHostToDevice));
+  return index_from_run_bytes(d_runs.as<uint8_t>(), n_runs, layout, slab_symbols, 0, out);
 }
 
 int bwtm_index_create_plain(const uint8_t* comps, uint64_t n, uint64_t slab_symbols, bwtm_index** out)

@@ -133,6 +133,14 @@ int bwtm_index_create_device(const void* rle_device, uint64_t rle_bytes, bwtm_in
    (formats.cpp:133-161): maximal runs (RunBuffer) -> Run::write -> samples. `slab_symbols` = symbols
    encoded per pass (0 = default). */
 int bwtm_index_create_plain(const uint8_t* comps, uint64_t n, uint64_t slab_symbols, bwtm_index** out);
+/* From one (comp, length) run per byte, lengths 1..31, decoded on the device: the counterpart of RopeData::read
+   (formats.cpp:286-310; layout BWTM_RUNS_ROPEBWT: byte = length << 3 | comp, the bytes after the 4-byte tag) and of
+   SGAData::read (formats.cpp:403-429; layout BWTM_RUNS_SGA: byte = comp << 5 | length, the bytes after the header).
+   Consecutive runs of one symbol are joined, as the reference's RunBuffer does. A byte with length 0 or a comp
+   value above 5 is refused (BWTM_ERR_ALPHABET). */
+#define BWTM_RUNS_ROPEBWT 0
+#define BWTM_RUNS_SGA     1
+int bwtm_index_create_runs(const uint8_t* runs, uint64_t n_runs, int layout, uint64_t slab_symbols, bwtm_index** out);
 int bwtm_index_destroy(bwtm_index* index);
 int bwtm_index_get_info(const bwtm_index* index, bwtm_index_info* info);
 /* Copies the RLE bytes to the host (what BlockArray::serialize, support.cpp:296-309, writes after

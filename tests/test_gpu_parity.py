@@ -377,3 +377,49 @@ def test_create_pair(oracle):
     assert np.array_equal(FMI.merge(DA, DB).rle(), oracle.merge(A, B).rle())
     with pytest.raises(bwtm_b200.BwtmError):
         FMI.from_rle_pair(A.rle(), np.zeros(0, dtype=np.uint8))
+
+
+def _run_bytes(comps, layout, rng=None):
+    """One (comp, length <= 31) run per byte; with rng the maximal runs are cut at random places as well."""
+    starts = np.concatenate([[0], np.flatnonzero(np.diff(comps)) + 1]); lengths = np.diff(np.concatenate([starts, [len(comps)]]))
+    out = []
+    for c, n in zip(comps[starts].tolist(), lengths.tolist()):
+        while n > 0:
+            take = min(31, n) if rng is None else int(rng.integers(1, min(31, n) + 1))
+            out.append((take << 3 | c) if layout == FMI.RUNS_ROPEBWT else (c << 5 | take)); n -= take
+    return np.array(out, dtype=np.uint8)
+
+
+@pytest.mark.parametrize("layout", [FMI.RUNS_ROPEBWT, FMI.RUNS_SGA])
+def test_run_byte_transcoder(oracle, tmp_path, layout):
+    """bwtm_index_create_runs: RopeData::read / SGAData::read on the device (formats.cpp:286-310, 403-429). Pieces of one
+    symbol are joined into maximal runs, as the reference's RunBuffer does, whatever way the file cut them."""
+    rng = np.random.default_rng(5)
+    for shape in ("reads", "noisy_N", "repeats", "single"):
+        bwt = collections(oracle, shape)[1]
+        if shape == "reads":   # long runs of every class as well
+            bwt = np.concatenate([bwt[:3000], np.full(70000, 2, np.uint8), bwt[3000:], np.full(43, 5, np.uint8), np.full(200, 0, np.uint8)])
+        want = oracle.from_comps(bwt)
+        for cut, slab in ((None, 0), (rng, 0), (rng, 4096)):
+            D = FMI.from_run_bytes(_run_bytes(bwt, layout, cut), layout, slab)
+            assert np.array_equal(D.rle(), want.rle()), (shape, slab)
+            assert np.array_equal(D.counts(), want.counts()) and D.size() == want.size and D.hash() == want.hash()
+        assert np.array_equal(D.extract(), bwt)
+    # a file written by the reference's own bwt_convert, when it is here
+    from oracle.oracle import REF_DIR, ref_available
+    if ref_available():
+        bwt = collections(oracle, "noisy_N")[1]
+        src, dst = str(tmp_path / "src.plain"), str(tmp_path / "dst.runs")
+        synth.comps_to_chars(bwt).tofile(src)
+        fmt = "ropebwt" if layout == FMI.RUNS_ROPEBWT else "sga"
+        subprocess.check_call([os.path.join(REF_DIR, "bwt_convert"), "-i", "plain_default", "-o", fmt, src, dst],
+                              stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        data = np.fromfile(dst, dtype=np.uint8)
+        # 4-byte tag / 30-byte SGA header (tag u16, sequences, bases, bytes u64, flags u32) that states the number of run bytes
+        body = data[4:] if layout == FMI.RUNS_ROPEBWT else data[30:30 + int(data[18:26].view(np.uint64)[0])]
+        assert np.array_equal(FMI.from_run_bytes(body, layout).rle(), oracle.from_comps(bwt).rle())
+    # refused: a zero-length run, a comp value of 6
+    bad = np.array([(3 << 3) | 1, 0 | 2, (6 << 3) | 6], dtype=np.uint8) if layout == FMI.RUNS_ROPEBWT else np.array([(1 << 5) | 3, (2 << 5), (6 << 5) | 6], dtype=np.uint8)
+    with pytest.raises(bwtm_b200.BwtmError) as err:
+        FMI.from_run_bytes(bad, layout)
+    assert err.value.code == -4
