@@ -101,6 +101,32 @@ DeviceFMI upload(HostBWT& host)
   return fmi;
 }
 
+// load(fmi, filename, format), fmi.cpp:373-409. RopeBWT and SGA files go to the device as they are and are decoded
+// there; a file the device reader refuses (zero-length codes) takes the host reader, which treats it
+// the way the reference does. The other formats are read on the host (PlainData::read joins equal characters, not
+// equal comp values, which only the host sees).
+DeviceFMI loadInput(const std::string& filename, const std::string& format)
+{
+  if(format == "ropebwt" || format == "sga")
+  {
+    std::vector<byte_type> runs;
+    if(!loadRunBytes(filename, format, runs)) { std::exit(EXIT_FAILURE); }
+    DeviceFMI fmi;
+    int rc = (runs.empty() ? BWTM_ERR_ALPHABET : bwtm_index_create_runs(runs.data(), runs.size(), (format == "sga" ? BWTM_RUNS_SGA : BWTM_RUNS_ROPEBWT), 0, &fmi.handle));
+    if(rc == BWTM_OK)
+    {
+      bwtm_index_info info; bwtm_index_get_info(fmi.handle, &info);
+      fmi.alpha = Alphabet::create(formatOrder(format)); fmi.alpha.setCounts(info.counts);
+      fmi.native_size = nativeSize(info.rle_bytes, info.bases, info.counts);
+      return fmi;
+    }
+    if(rc != BWTM_ERR_ALPHABET) { fail("load()"); }
+  }
+  HostBWT host;
+  if(!loadBWT(host, filename, format)) { std::exit(EXIT_FAILURE); }
+  return upload(host);
+}
+
 // verifyFMI + queryFMI (bwt_merge.cpp:240-285): adds the occurrences of every pattern to results.
 void verifyFMI(const DeviceFMI& fmi, const std::string& name, const std::vector<std::string>& patterns, std::vector<size_type>& results)
 {
@@ -203,19 +229,16 @@ int main(int argc, char** argv)
 
   if(bwtm_set_device(0) != BWTM_OK) { fail("bwt_merge"); }
 
-  HostBWT host;
-  if(!loadBWT(host, argv[optind], input_formats[0])) { std::exit(EXIT_FAILURE); }
-  DeviceFMI index = upload(host);
+  DeviceFMI index = loadInput(argv[optind], input_formats[0]);
   verifyFMI(index, "Input", patterns, pre_results);
 
   size_type bytes_added = 0;
   for(int input = 1; input < inputs; input++)
   {
-    HostBWT next;
-    if(!loadBWT(next, argv[optind + input], input_formats[input])) { std::exit(EXIT_FAILURE); }
-    size_type increment_size = next.bases;
+    DeviceFMI increment = loadInput(argv[optind + input], input_formats[input]);
+    size_type increment_size = 0;
+    { bwtm_index_info info; bwtm_index_get_info(increment.handle, &info); increment_size = info.bases; }
     bytes_added += increment_size;
-    DeviceFMI increment = upload(next);
     verifyFMI(increment, "Input", patterns, pre_results);
 
     // merge(), bwt_merge.cpp:287-299

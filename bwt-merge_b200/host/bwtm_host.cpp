@@ -522,6 +522,33 @@ bool loadBWT(HostBWT& bwt, const std::string& filename, const std::string& forma
   return true;
 }
 
+// The run bytes of a RopeBWT or SGA file as they are (one (comp, length) code per byte), for the device-side
+// reader bwtm_index_create_runs. Same header checks and messages as loadBWT.
+bool loadRunBytes(const std::string& filename, const std::string& format, std::vector<byte_type>& runs)
+{
+  runs.clear();
+  std::ifstream in(filename.c_str(), std::ios_base::binary);
+  if(!in) { std::cerr << "BWT::load(): Cannot open input file " << filename << std::endl; return false; }
+  size_type bytes = 0;
+  if(format == "ropebwt")
+  {
+    std::uint32_t tag = 0; readPod(in, tag);
+    if(!in || tag != 0x06454C52u) { std::cerr << "RopeFormat::load(): Invalid header!" << std::endl; return false; }
+    bytes = remainingBytes(in);
+  }
+  else if(format == "sga")
+  {
+    std::uint16_t tag = 0; size_type sequences = 0, bases = 0; std::uint32_t flags = 0;
+    readPod(in, tag); readPod(in, sequences); readPod(in, bases); readPod(in, bytes); readPod(in, flags);
+    if(!in || tag != 0xCACA || flags != 0) { std::cerr << "SGAFormat::load(): Invalid header!" << std::endl; return false; }
+  }
+  else { std::cerr << "load(): Invalid BWT format: " << format << std::endl; return false; }
+  runs.resize(bytes);
+  in.read(reinterpret_cast<char*>(runs.data()), bytes);
+  runs.resize(in.gcount() > 0 ? (size_type)in.gcount() : 0);
+  return true;
+}
+
 bool serializeBWT(const HostBWT& bwt, const std::string& filename, const std::string& format)
 {
   if(!formatExists(format)) { std::cerr << "serialize(): Invalid BWT format: " << format << std::endl; return false; }

@@ -96,6 +96,8 @@ std::string formatName(const std::string& tag);
 // printing the reference's message to stderr when the file cannot be opened or has a bad header.
 bool loadBWT(HostBWT& bwt, const std::string& filename, const std::string& format);
 bool serializeBWT(const HostBWT& bwt, const std::string& filename, const std::string& format);
+// Raw run bytes of a RopeBWT / SGA file (header checked and skipped) for the device-side reader.
+bool loadRunBytes(const std::string& filename, const std::string& format, std::vector<byte_type>& runs);
 
 // Reporting helpers with the reference's formatting (utils.cpp:38-96).
 void printHeader(const std::string& header, size_type indent = 18);
