@@ -24,10 +24,13 @@ u64p = C.POINTER(C.c_uint64)
 
 
 def build(ref=True):
-    """Compile the C restatement and, when the reference sources are present, oracle/_ref."""
+    """Compile the C restatement and, when the reference sources are present, oracle/_ref (and, once the product
+    library exists, the reference's own bwt_merge bound to it: target ref_b200)."""
     subprocess.check_call(["make", "-s", "-C", HERE, "oracle"])
     if ref and os.path.isdir(REFERENCE_SRC):
         subprocess.check_call(["make", "-s", "-C", HERE, "-j8", "ref"])
+        if os.path.exists(os.path.join(HERE, "..", "bwt-merge_b200", "lib", "libbwtm_b200.so")):
+            subprocess.check_call(["make", "-s", "-C", HERE, "ref_b200"])
 
 
 def ref_available():

@@ -45,3 +45,28 @@ def test_no_cpu_fallback(library):
         bwtm_b200.FMI.from_rle(rle)
     assert err.value.code == -2
     assert "no CPU fallback" in str(err.value)
+
+
+def test_reference_cli_links_the_abi_and_has_no_cpu_fallback(library, oracle, tmp_path):
+    """oracle/_ref/bwt_merge_b200 is the reference's own bwt_merge.cpp with FMI::FMI(FMI&, FMI&, MergeParameters)
+    (fmi.cpp:336-369) replaced by bwt-merge_b200/integration/fmi_b200.cpp: it must import the C ABI and, without a
+    device, stop with the library's error instead of merging on the CPU."""
+    import subprocess
+    import torch
+    from bwtm_b200 import synth
+    from conftest import make_collection
+    tool = os.path.join(ROOT, "oracle", "_ref", "bwt_merge_b200")
+    if not os.path.exists(tool):
+        pytest.skip("oracle/_ref/bwt_merge_b200 not built (reference sources absent)")
+    symbols = subprocess.run(["nm", "-D", "--undefined-only", tool], capture_output=True, text=True).stdout
+    for name in ("bwtm_index_create_pair", "bwtm_merge", "bwtm_index_download"):
+        assert name in symbols
+    if torch.cuda.is_available():
+        return
+    paths = []
+    for k in (1, 2):
+        _, bwt = make_collection(oracle, 2000, 60, 40, 0.01, 42, k)
+        paths.append(str(tmp_path / ("in%d.plain" % k))); synth.comps_to_chars(bwt).tofile(paths[-1])
+    res = subprocess.run([tool, "-i", "plain_default", "-o", "plain_default"] + paths + [str(tmp_path / "out")],
+                         capture_output=True, text=True, timeout=120)
+    assert res.returncode != 0 and "no CPU fallback" in res.stderr

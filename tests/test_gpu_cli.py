@@ -1,5 +1,9 @@
-"""bwt_merge_b200 (host driver above the C ABI) against the unmodified reference binary oracle/_ref/bwt_merge:
-same files, same -v report."""
+"""Two command lines above the C ABI against the unmodified reference binary oracle/_ref/bwt_merge (same files,
+same -v report):
+  * bin/bwt_merge_b200          -- the product's host driver;
+  * oracle/_ref/bwt_merge_b200  -- the REFERENCE's own bwt_merge.cpp and libraries, unmodified, with only the merging
+                                   constructor FMI::FMI(FMI&, FMI&, MergeParameters) bound to libbwtm_b200.so by
+                                   bwt-merge_b200/integration/fmi_b200.cpp (oracle/Makefile, target ref_b200)."""
 import filecmp
 import os
 import re
@@ -13,6 +17,8 @@ from conftest import ROOT, make_collection
 
 pytestmark = pytest.mark.gpu
 MINE = os.path.join(ROOT, "bwt-merge_b200", "bin", "bwt_merge_b200")
+REF_OVER_ABI = os.path.join(ROOT, "oracle", "_ref", "bwt_merge_b200")
+TOOLS = {"host_driver": MINE, "reference_cli_over_abi": REF_OVER_ABI}
 
 
 def report(stdout):
@@ -30,11 +36,15 @@ def report(stdout):
     return keep
 
 
+@pytest.mark.parametrize("tool", list(TOOLS))
 @pytest.mark.parametrize("fmt_in,fmt_out", [("plain_default", "native"), ("native", "plain_default"), ("sga", "ropebwt"), ("ropebwt", "sga")])
-def test_cli_matches_reference(oracle, tmp_path, fmt_in, fmt_out):
+def test_cli_matches_reference(oracle, tmp_path, fmt_in, fmt_out, tool):
     from oracle.oracle import REF_DIR, ref_available
     if not ref_available():
         pytest.skip("oracle/_ref not present")
+    under_test = TOOLS[tool]
+    if not os.path.exists(under_test):
+        pytest.skip("%s not built" % under_test)
     ref_merge, ref_convert = os.path.join(REF_DIR, "bwt_merge"), os.path.join(REF_DIR, "bwt_convert")
     inputs = []
     for k, n in enumerate((500, 300, 120)):
@@ -50,9 +60,9 @@ def test_cli_matches_reference(oracle, tmp_path, fmt_in, fmt_out):
             f.write(synth.comps_to_chars(p).tobytes().decode() + "\n")
         f.write("\nNNNNNN\nACGT\n")
     outs = []
-    for tool, name in ((MINE, "mine"), (ref_merge, "ref")):
+    for binary, name in ((under_test, "mine"), (ref_merge, "ref")):
         out = str(tmp_path / (name + "." + fmt_out))
-        res = subprocess.run([tool, "-t", "4", "-r", "1", "-b", "1", "-d", str(tmp_path), "-v", patterns, "-i", fmt_in, "-o", fmt_out]
+        res = subprocess.run([binary, "-t", "4", "-r", "1", "-b", "1", "-d", str(tmp_path), "-v", patterns, "-i", fmt_in, "-o", fmt_out]
                              + inputs + [out], capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stderr[-2000:]
         outs.append((out, res.stdout.replace(out, "OUTPUT")))
