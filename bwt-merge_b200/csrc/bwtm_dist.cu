@@ -112,6 +112,7 @@ struct bwtm_comm
   int        peer_state;            // 0 not tried yet, 1 windows usable, -1 not available: NCCL moves the data
   PeerWindow key_window, rle_window;
   unsigned long long* d_flag;       // scratch of the barrier
+  long long* d_status;              // scratch of agree_on_status
 };
 
 namespace bwtm
@@ -173,6 +174,20 @@ static int stream_barrier(bwtm_comm* comm, cudaStream_t stream)
 {
   BWTM_NCCL(nccl()->AllReduce(comm->d_flag, comm->d_flag, 1, ncclUint64, ncclMax, comm->comm, stream));
   return BWTM_OK;
+}
+
+// The merge is a collective: a rank that fails locally (allocation, capacity, invalid input) must not leave the
+// others waiting in the next all-reduce or receive. Every phase that can fail on one rank alone ends here: the
+// smallest status code of all ranks becomes everybody's status, so all ranks return together with an error.
+static int agree_on_status(bwtm_comm* comm, int rc, cudaStream_t stream, const char* phase)
+{
+  long long mine = rc, all = rc;
+  if(cudaMemcpyAsync(comm->d_status, &mine, sizeof(mine), cudaMemcpyHostToDevice, stream) != cudaSuccess) { return cuda_failed(cudaGetLastError(), "status upload", __FILE__, __LINE__); }
+  BWTM_NCCL(nccl()->AllReduce(comm->d_status, comm->d_status, 1, ncclInt64, ncclMin, comm->comm, stream));
+  BWTM_CUDA(cudaMemcpyAsync(&all, comm->d_status, sizeof(all), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  if(all != BWTM_OK && rc == BWTM_OK) { set_error("distributed merge stopped after '%s': another rank failed with status %lld", phase, all); }
+  return (int)all;
 }
 
 static void window_close(bwtm_comm* comm, PeerWindow* window)
@@ -298,28 +313,34 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   uint64_t capacity = std::min<uint64_t>(n_b, (uint64_t)((double)n_b * ((double)seq_count / (double)m_b) * 1.25) + (1ull << 20));
   DeviceBuffer keys, alt;
   uint64_t local_n = 0;
-  timer.start();
-  for(int attempt = 0; attempt < 2; attempt++)
-  {
-    BWTM_TRY(keys.allocate(std::max<uint64_t>(capacity, 1) * sizeof(KeyT)));
-    if(seq_count == 0) { break; }
-    int rc = walk_sequences<KeyT>(a, b, seq_first, seq_first + seq_count - 1, keys.as<KeyT>(), capacity, &local_n, stream);
-    if(rc == BWTM_OK) { break; }
-    if(rc != BWTM_ERR_CAPACITY || attempt == 1 || capacity == n_b) { return rc; }
-    capacity = n_b;   // sequences of very different lengths: take the upper bound
-  }
-  timings->search_seconds = timer.stop() * 1e-3;
-  timings->walk_kernel_launches = (seq_count > 0 ? 1 : 0);
-
-  timer.start();
   const int bits = bit_length_host(n_a);
-  KeyT* sorted = keys.as<KeyT>();
-  if(local_n > 0)
+  KeyT* sorted = nullptr;
+  auto search_and_sort = [&]() -> int
   {
-    BWTM_TRY(alt.allocate(local_n * sizeof(KeyT)));
-    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), local_n, bits, &sorted, stream, n_a + 1));
-  }
-  timings->sort_seconds = timer.stop() * 1e-3;
+    timer.start();
+    for(int attempt = 0; attempt < 2; attempt++)
+    {
+      BWTM_TRY(keys.allocate(std::max<uint64_t>(capacity, 1) * sizeof(KeyT)));
+      if(seq_count == 0) { break; }
+      int rc = walk_sequences<KeyT>(a, b, seq_first, seq_first + seq_count - 1, keys.as<KeyT>(), capacity, &local_n, stream);
+      if(rc == BWTM_OK) { break; }
+      if(rc != BWTM_ERR_CAPACITY || attempt == 1 || capacity == n_b) { return rc; }
+      capacity = n_b;   // sequences of very different lengths: take the upper bound
+    }
+    timings->search_seconds = timer.stop() * 1e-3;
+    timings->walk_kernel_launches = (seq_count > 0 ? 1 : 0);
+
+    timer.start();
+    sorted = keys.as<KeyT>();
+    if(local_n > 0)
+    {
+      BWTM_TRY(alt.allocate(local_n * sizeof(KeyT)));
+      BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), local_n, bits, &sorted, stream, n_a + 1));
+    }
+    timings->sort_seconds = timer.stop() * 1e-3;
+    return BWTM_OK;
+  };
+  BWTM_TRY(agree_on_status(comm, search_and_sort(), stream, "search and local sort"));
   phase.mark("walk + local sort");
 
   // 2. splitters: smallest p with p + #{keys < p} >= k (n_a + n_b) / G
@@ -379,7 +400,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   if(P > 0)
   {
     BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, splitter.data() + 1, P * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-    lower_bounds<KeyT><<<1, 32, 0, stream>>>(sorted, local_n, d_probes.as<unsigned long long>(), P, d_counts.as<unsigned long long>());
+    lower_bounds<KeyT><<<(unsigned)div_up(P, 32), 32, 0, stream>>>(sorted, local_n, d_probes.as<unsigned long long>(), P, d_counts.as<unsigned long long>());
     BWTM_LAUNCH_CHECK();
     BWTM_CUDA(cudaMemcpyAsync(send_offset.data() + 1, d_counts.ptr, P * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
     BWTM_CUDA(cudaStreamSynchronize(stream));
@@ -447,7 +468,7 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   }
   else
   {
-    BWTM_TRY(received.allocate(std::max<uint64_t>(recv_total, 1) * sizeof(KeyT)));
+    BWTM_TRY(agree_on_status(comm, received.allocate(std::max<uint64_t>(recv_total, 1) * sizeof(KeyT)), stream, "receive buffer"));
     BWTM_NCCL(api->GroupStart());
     for(int peer = 0; peer < G; peer++)
     {
@@ -462,15 +483,14 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   phase.mark("all-to-all");
   keys.release(); alt.release();
   KeyT* slice_keys = arrived;
-  if(recv_total > 0 && G > 1)
+  auto merge_received = [&]() -> int
   {
+    if(recv_total == 0 || G == 1) { return BWTM_OK; }
     BWTM_TRY(received_alt.allocate(recv_total * sizeof(KeyT)));
-    if(recv_total < 0x7FFFFFFFull)
-    {
-      BWTM_TRY(merge_sorted_pieces<KeyT>(arrived, received_alt.as<KeyT>(), recv_offset, stream, &slice_keys));
-    }
-    else { BWTM_TRY(sort_keys<KeyT>(arrived, received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream)); }
-  }
+    if(recv_total < 0x7FFFFFFFull) { return merge_sorted_pieces<KeyT>(arrived, received_alt.as<KeyT>(), recv_offset, stream, &slice_keys); }
+    return sort_keys<KeyT>(arrived, received_alt.as<KeyT>(), recv_total, bits, &slice_keys, stream);
+  };
+  int merge_rc = merge_received();
   timings->exchange_seconds = timer.stop() * 1e-3;
   phase.mark("sort received");
 
@@ -492,10 +512,12 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   DeviceBuffer tile_j, control;
   std::vector<DeviceBuffer> merged(parallel ? n_slabs : 0);   // plane chunks of every slab, read again by emit()
   std::vector<SlabEncoder> encoders(parallel ? n_slabs : 1);
-  BWTM_TRY(control.allocate(sizeof(EncodeControl)));
   float interleave_ms = 0.0f, encode_ms = 0.0f;
-  if(parallel)
+  auto interleave_slabs = [&]() -> int
   {
+    BWTM_TRY(merge_rc);
+    BWTM_TRY(control.allocate(sizeof(EncodeControl)));
+    if(!parallel) { return BWTM_OK; }
     BWTM_TRY(tile_j.allocate((slab / interleave_tile_size() + 2) * sizeof(uint64_t)));
     for(uint64_t k = 0; k < n_slabs; k++)
     {
@@ -509,7 +531,9 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
       BWTM_TRY(encoders[k].detect(merged[k].as<uint4>(), p1 - p0, stream));
       encode_ms += timer.stop();
     }
-  }
+    return BWTM_OK;
+  };
+  BWTM_TRY(agree_on_status(comm, interleave_slabs(), stream, "merge of the received values and interleave"));
   phase.mark("interleave + runs");
 
   // 7. the writer state comes from the previous slice and goes to the next one
@@ -521,9 +545,15 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   EncodeControl ctl;
   BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
-  OutputBuffer out = { nullptr, 0, ctl.out_size, nullptr };
+  // A rank that failed earlier in the chain passes POISONED_STATE on: the ranks after it skip their part but keep
+  // the chain moving, and everybody learns the status in agree_on_status below.
+  const unsigned long long POISONED_STATE = ~0ull;
+  bool upstream_failed = (ctl.out_size == POISONED_STATE);
+  OutputBuffer out = { nullptr, 0, (upstream_failed ? 0 : ctl.out_size), nullptr };
   uint64_t estimate = (a->rle_bytes + b->rle_bytes) / G;
-  int rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream);
+  int rc = BWTM_OK;
+  if(upstream_failed) { set_error("an earlier rank of the writer chain failed"); rc = BWTM_ERR_COMM; }
+  else { rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream); }
   timer.start();
   if(rc == BWTM_OK && slice > 0)
   {
@@ -537,7 +567,12 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
                                   control.as<EncodeControl>(), false, &interleave_ms, &encode_ms, stream);
     }
   }
-  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  if(rc != BWTM_OK && !upstream_failed)
+  {
+    EncodeControl poisoned; std::memset(&poisoned, 0, sizeof(poisoned)); poisoned.out_size = POISONED_STATE;
+    cudaMemcpyAsync(control.ptr, &poisoned, sizeof(poisoned), cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);
+  }
   // The next slice only needs the state after this one: it goes out before the bytes are written.
   if(r < G - 1) { BWTM_NCCL(api->Send(control.ptr, sizeof(EncodeControl), ncclUint8, r + 1, comm->comm, stream)); }
   if(parallel)
@@ -549,8 +584,9 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
     if(!parallel) { rc = encoders[0].init(4096, stream); }
     if(rc == BWTM_OK) { rc = encoders[0].finish(&out, control.as<EncodeControl>(), stream); }
   }
-  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   if(parallel) { encode_ms += timer.stop(); } else { timer.stop(); }
+  rc = agree_on_status(comm, rc, stream, "chained writer");
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   timings->interleave_seconds = interleave_ms * 1e-3;
@@ -593,8 +629,8 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   }
   else
   {
-    rc = ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream);
-    if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+    rc = agree_on_status(comm, ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream), stream, "gather buffer");
+    if(rc != BWTM_OK) { device_free(out.ptr); device_free(full.ptr); return rc; }
     for(int k = 0; k < G; k++)
     {
       uint64_t offset = slices[(size_t)3 * k], bytes = slices[(size_t)3 * k + 1];
@@ -664,12 +700,13 @@ int bwtm_comm_create(const uint8_t* id, int rank, int world, bwtm_comm** out)
   BWTM_NCCL(api->CommInitRank(&comm, world, unique, rank));
   bwtm_comm* c = new bwtm_comm();
   c->comm = comm; c->rank = rank; c->world = world;
-  c->peer_state = 0; c->d_flag = nullptr;
-  if(cudaMalloc(reinterpret_cast<void**>(&(c->d_flag)), sizeof(unsigned long long)) != cudaSuccess || cudaMemset(c->d_flag, 0, sizeof(unsigned long long)) != cudaSuccess)
+  c->peer_state = 0; c->d_flag = nullptr; c->d_status = nullptr;
+  if(cudaMalloc(reinterpret_cast<void**>(&(c->d_flag)), 2 * sizeof(unsigned long long)) != cudaSuccess || cudaMemset(c->d_flag, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
   {
     cudaGetLastError(); api->CommDestroy(comm); delete c;
     set_error("cannot allocate the barrier word"); return BWTM_ERR_MEMORY;
   }
+  c->d_status = reinterpret_cast<long long*>(c->d_flag + 1);
   *out = c;
   return BWTM_OK;
 }

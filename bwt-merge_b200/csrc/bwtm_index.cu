@@ -728,9 +728,18 @@ int bwtm_index_download(const bwtm_index* index, uint8_t* out_rle, uint64_t capa
   return BWTM_OK;
 }
 
+// Every query reads the rank records: an index built with skip_index has none (RLE bytes only).
+static int require_records(const bwtm_index* index)
+{
+  if(index->d_records != nullptr) { return BWTM_OK; }
+  set_error("the index has no rank structure (it was built with skip_index): only info and download are available");
+  return BWTM_ERR_ARGUMENT;
+}
+
 int bwtm_index_samples(const bwtm_index* index, uint64_t* block_ends, uint64_t* cumulative, uint64_t blocks)
 {
   if(index == nullptr || block_ends == nullptr || cumulative == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  BWTM_TRY(require_records(index));
   uint64_t expected = div_up(index->rle_bytes, RLE_BLOCK);
   if(blocks != expected) { set_error("the index has %llu blocks", (unsigned long long)expected); return BWTM_ERR_ARGUMENT; }
   DeviceBuffer starts; BWTM_TRY(starts.allocate((blocks + 1) * sizeof(uint64_t)));
@@ -748,6 +757,7 @@ int bwtm_index_samples(const bwtm_index* index, uint64_t* block_ends, uint64_t* 
 int bwtm_index_extract(const bwtm_index* index, uint64_t first, uint64_t count, uint8_t* out_comps)
 {
   if(index == nullptr || out_comps == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  BWTM_TRY(require_records(index));
   if(first > index->size || count > index->size - first) { set_error("range out of bounds"); return BWTM_ERR_ARGUMENT; }
   if(count == 0) { return BWTM_OK; }
   DeviceBuffer out; BWTM_TRY(out.allocate(count));
@@ -760,6 +770,7 @@ int bwtm_index_extract(const bwtm_index* index, uint64_t first, uint64_t count, 
 int bwtm_index_hash(const bwtm_index* index, uint64_t* hash)
 {
   if(index == nullptr || hash == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  BWTM_TRY(require_records(index));
   // FNV-1a is inherently sequential; the symbols are extracted on the device and folded on the host.
   const uint64_t CHUNK = 64ull << 20;
   std::vector<uint8_t> buffer(index->size < CHUNK ? index->size : CHUNK);
@@ -777,6 +788,7 @@ int bwtm_index_hash(const bwtm_index* index, uint64_t* hash)
 int bwtm_rank(const bwtm_index* index, const uint64_t* positions, const uint8_t* comps, uint64_t n, uint64_t* out_ranks)
 {
   if(index == nullptr || positions == nullptr || comps == nullptr || out_ranks == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  BWTM_TRY(require_records(index));
   if(n == 0) { return BWTM_OK; }
   DeviceBuffer pos, cmp, res;
   BWTM_TRY(pos.allocate(n * 8)); BWTM_TRY(cmp.allocate(n)); BWTM_TRY(res.allocate(n * 8));
@@ -791,6 +803,7 @@ int bwtm_rank(const bwtm_index* index, const uint64_t* positions, const uint8_t*
 int bwtm_lf(const bwtm_index* index, const uint64_t* positions, uint64_t n, uint64_t* out_positions, uint8_t* out_comps)
 {
   if(index == nullptr || positions == nullptr || out_positions == nullptr || out_comps == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  BWTM_TRY(require_records(index));
   if(n == 0) { return BWTM_OK; }
   DeviceBuffer pos, res, cmp;
   BWTM_TRY(pos.allocate(n * 8)); BWTM_TRY(res.allocate(n * 8)); BWTM_TRY(cmp.allocate(n));
@@ -806,6 +819,7 @@ int bwtm_count(const bwtm_index* index, const uint8_t* patterns, const uint64_t*
                const uint8_t* char2comp, uint64_t* out_counts)
 {
   if(index == nullptr || offsets == nullptr || out_counts == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
+  BWTM_TRY(require_records(index));
   if(n == 0) { return BWTM_OK; }
   uint64_t total = offsets[n];
   if(total > 0 && patterns == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }

@@ -1587,6 +1587,7 @@ int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first
 {
   if(a == nullptr || b == nullptr || out_sorted == nullptr || n_values == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
   if(seq_first > seq_last || seq_last >= b->sequences) { set_error("invalid sequence range"); return BWTM_ERR_ARGUMENT; }
+  if(a->d_records == nullptr || b->d_records == nullptr) { set_error("an input has no rank structure (it was built with skip_index)"); return BWTM_ERR_ARGUMENT; }
   DeviceBuffer keys, alt;
   BWTM_TRY(keys.allocate(capacity * sizeof(uint64_t)));
   BWTM_TRY(alt.allocate(capacity * sizeof(uint64_t)));

@@ -382,7 +382,9 @@ static void writeSymbols(std::ofstream& out, const HostBWT& bwt, const Alphabet&
 }
 
 // RopeData::read (formats.cpp:286-310): (comp, length) codes, coalesced into maximal runs.
-static void readRuns(std::ifstream& in, size_type bytes, bool sga, HostBWT& bwt)
+// Returns false on a comp value above 5: the reference would index past its count array with it (RunBuffer::add,
+// Run::write), here it is a malformed file.
+static bool readRuns(std::ifstream& in, size_type bytes, bool sga, HostBWT& bwt)
 {
   RunWriter writer(bwt.rle);
   std::vector<byte_type> buffer(MEGABYTE);
@@ -393,12 +395,18 @@ static void readRuns(std::ifstream& in, size_type bytes, bool sga, HostBWT& bwt)
     for(size_type i = 0; i < n; i++)
     {
       size_type comp = (sga ? buffer[i] >> 5 : buffer[i] & 0x07), length = (sga ? buffer[i] & 0x1F : buffer[i] >> 3);
+      if(comp >= SIGMA)
+      {
+        std::cerr << (sga ? "SGAFormat" : "RopeFormat") << "::load(): Invalid character value " << comp << " at run " << (offset + i) << std::endl;
+        return false;
+      }
       // RunBuffer::add(v, n) (utils.h:125-134): a run of another value flushes the pending one, even if n == 0.
       writer.add(comp, length);
     }
   }
   writer.finish();
   for(size_type c = 0; c < SIGMA; c++) { bwt.counts[c] = writer.counts[c]; }
+  return true;
 }
 
 static size_type countShortRuns(const HostBWT& bwt)   // RopeData::countRuns, formats.cpp:343-363
@@ -508,14 +516,14 @@ bool loadBWT(HostBWT& bwt, const std::string& filename, const std::string& forma
   {
     std::uint32_t tag = 0; readPod(in, tag);
     if(!in || tag != 0x06454C52u) { std::cerr << "RopeFormat::load(): Invalid header!" << std::endl; return false; }
-    readRuns(in, remainingBytes(in), false, bwt);
+    if(!readRuns(in, remainingBytes(in), false, bwt)) { return false; }
   }
   else if(format == "sga")
   {
     std::uint16_t tag = 0; size_type sequences = 0, bases = 0, bytes = 0; std::uint32_t flags = 0;
     readPod(in, tag); readPod(in, sequences); readPod(in, bases); readPod(in, bytes); readPod(in, flags);
     if(!in || tag != 0xCACA || flags != 0) { std::cerr << "SGAFormat::load(): Invalid header!" << std::endl; return false; }
-    readRuns(in, bytes, true, bwt);
+    if(!readRuns(in, std::min(bytes, remainingBytes(in)), true, bwt)) { return false; }
   }
   else { std::cerr << "load(): Invalid BWT format: " << format << std::endl; return false; }
   finishLoaded(bwt, formatOrder(format));
@@ -541,6 +549,7 @@ bool loadRunBytes(const std::string& filename, const std::string& format, std::v
     std::uint16_t tag = 0; size_type sequences = 0, bases = 0; std::uint32_t flags = 0;
     readPod(in, tag); readPod(in, sequences); readPod(in, bases); readPod(in, bytes); readPod(in, flags);
     if(!in || tag != 0xCACA || flags != 0) { std::cerr << "SGAFormat::load(): Invalid header!" << std::endl; return false; }
+    bytes = std::min(bytes, remainingBytes(in));   // the header is not trusted with the allocation
   }
   else { std::cerr << "load(): Invalid BWT format: " << format << std::endl; return false; }
   runs.resize(bytes);
