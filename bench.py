@@ -76,6 +76,8 @@ def parse_args():
     ap.add_argument("--record-digest", action="store_true", help="reference arm: store the digest of its result in tests/golden/")
     ap.add_argument("--digest-out", default=None, help="reference arm: also write the digest entry to this file")
     ap.add_argument("--reference-prefix-only", action="store_true", help="reference arm: only the bounded sample (no full run)")
+    ap.add_argument("--walk", default="auto", choices=["auto", "single", "pairs"],
+                    help="rank/LF walk: 64-byte records, one step per read (single) or 128-byte pair records, two steps per read (pairs)")
     ap.add_argument("--gather-bench", action="store_true", help="measure the random-access HBM peak as well")
     args = ap.parse_args()
     for key, value in CONFIGS[args.config].items():
@@ -349,6 +351,17 @@ def main():
     info_a, info_b = A.info(), B.info()
     assert info_a.bases == n_a and info_b.bases == n_b
 
+    # The pair records (two backward steps per record read) belong to an index like the basic rank records K0 builds:
+    # for the device-timed `value` they are resident with the inputs. (The e2e legs below start from host bytes and pay
+    # for every structure they use inside the timed region.)
+    if args.walk != "auto":
+        os.environ["BWTM_WALK"] = args.walk
+    pair_build_ms = None
+    if args.walk != "single":
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        A.build_pairs(); B.build_pairs()
+        torch.cuda.synchronize(); pair_build_ms = (time.perf_counter() - t0) * 1e3
+
     comm = None
     if world > 1:
         comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
@@ -405,7 +418,7 @@ def main():
     barrier()
     sampler.start()
     launches0 = bwtm_b200.kernel_launches()
-    stage = {k: 0.0 for k in ("search", "sort", "exchange", "interleave", "encode", "index")}
+    stage = {k: 0.0 for k in ("search", "sort", "exchange", "interleave", "encode", "index", "pair_index")}
     last = None
     # Inputs smaller than twice the L2 would stay cached between steps: flush it (outside the timed events).
     flush = None
@@ -518,7 +531,7 @@ def main():
         # MISSES; the kernel's requests are compared with it after removing the share that hits in L2 (ncu, committed).
         table = int(last.get("walk_table_bytes", 0)) or int(info_a.device_bytes + info_b.device_bytes)
         record_bytes = int(last.get("walk_record_bytes", 0)) or 64
-        requests_per_base = float(last.get("walk_requests_per_base", 0)) or 2.0
+        requests_per_base = (1.0 if record_bytes == 128 else 2.0)   # one record of each index per step; a pair record answers two steps
         peak_records = bwtm_b200.chase_bench(max(table, 1 << 28), record_bytes, 1 << 28, 2048) / float(record_bytes)
         achieved_records = requests_per_base * (n_b / world) / k1_s / 1e9 if k1_s > 0 else 0.0
         l2_hit = None
@@ -558,6 +571,11 @@ def main():
         "dtype": "u64", "data": "synthetic",
         "config": config_dict(args, n_a, n_b, [info_a.rle_bytes, info_b.rle_bytes, merged_bytes]),
         "input_build_seconds": t_build, "steps_ms": [round(x, 2) for x in step_ms_device],
+        "walk": {"record_bytes": int(last["walk_record_bytes"]), "table_bytes": int(last["walk_table_bytes"]),
+                 "search_batches": int(last["search_batches"]),
+                 "pair_records_build_ms": pair_build_ms,
+                 "note": "pair records of both inputs built once before the timed region (bwtm_index_build_pairs), like K0; "
+                         "e2e builds them inside its timed region" if pair_build_ms is not None else "single-step walk"},
         "verified": verified,
         "stages_ms": {k: v * 1e3 for k, v in stage.items()},
         "stage_bases_per_second": {k: (n_b / v if v > 0 else None) for k, v in stage.items()},

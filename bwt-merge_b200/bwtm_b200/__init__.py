@@ -27,7 +27,7 @@ EXPORTS = [
     "bwtm_last_error", "bwtm_version", "bwtm_device_count", "bwtm_set_device", "bwtm_kernel_launches",
     "bwtm_index_create", "bwtm_index_create_pair", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_create_runs", "bwtm_index_destroy", "bwtm_index_get_info",
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
-    "bwtm_rank", "bwtm_lf", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
+    "bwtm_index_build_pairs", "bwtm_rank", "bwtm_lf", "bwtm_lf2", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
     "bwtm_shard_range", "bwtm_comm_unique_id", "bwtm_comm_create", "bwtm_comm_destroy", "bwtm_merge_distributed",
     "bwtm_tools_build_synthetic", "bwtm_tools_build_from_reads", "bwtm_tools_gather_bench", "bwtm_tools_chase_bench",
 ]
@@ -57,7 +57,8 @@ class Timings(C.Structure):
                 ("interleave_seconds", C.c_double), ("encode_seconds", C.c_double), ("index_seconds", C.c_double),
                 ("total_seconds", C.c_double), ("ra_values", C.c_uint64), ("ra_runs", C.c_uint64),
                 ("merged_runs", C.c_uint64), ("merged_bytes", C.c_uint64), ("walk_kernel_launches", C.c_uint64),
-                ("kernel_launches", C.c_uint64)]
+                ("kernel_launches", C.c_uint64), ("pair_index_seconds", C.c_double), ("walk_record_bytes", C.c_uint64),
+                ("walk_table_bytes", C.c_uint64), ("search_batches", C.c_uint64)]
 
     def as_dict(self):
         return {name: getattr(self, name) for name, _ in self._fields_}
@@ -106,6 +107,8 @@ def lib():
     L.bwtm_index_hash.argtypes = [vp, u64p]
     L.bwtm_rank.argtypes = [vp, u64p, u8p, C.c_uint64, u64p]
     L.bwtm_lf.argtypes = [vp, u64p, C.c_uint64, u64p, u8p]
+    L.bwtm_index_build_pairs.argtypes = [vp]
+    L.bwtm_lf2.argtypes = [vp, u64p, C.c_uint64, u64p, u64p, u8p]
     L.bwtm_count.argtypes = [vp, u8p, u64p, C.c_uint64, u8p, u64p]
     L.bwtm_merge.argtypes = [vp, vp, C.POINTER(MergeOptions), C.POINTER(vp), C.POINTER(Timings)]
     L.bwtm_rank_array.argtypes = [vp, vp, C.c_uint64, C.c_uint64, u64p, C.c_uint64, u64p]
@@ -151,7 +154,7 @@ class MergeParameters:
         self.thread_buffer_size = self.THREAD_BUFFER_SIZE
         self.merge_buffers = self.MERGE_BUFFERS
         self.threads = 1
-        self.sequence_blocks = 1
+        self.sequence_blocks = 0     # 0: batches chosen from the free device memory (include/bwtm.h)
         self.temp_dir = "."
         self.slab_symbols = 0
         self.skip_index = False
@@ -315,6 +318,18 @@ class FMI:
         out = np.zeros(len(positions), dtype=np.uint64); oc = np.zeros(len(positions), dtype=np.uint8)
         check(lib().bwtm_lf(self._h, _p(positions, u64p), len(positions), _p(out, u64p), _p(oc, u8p)))
         return out, oc
+
+    def build_pairs(self):
+        """Pair records for the two-step walk, built now instead of on first use as a merge input."""
+        check(lib().bwtm_index_build_pairs(self._h)); return self
+
+    def LF2(self, positions):
+        """Two backward steps from the pair records: (LF(i), LF(LF(i)), BWT[i], BWT[LF(i)])."""
+        positions = np.ascontiguousarray(positions, dtype=np.uint64)
+        first = np.zeros(len(positions), dtype=np.uint64); second = np.zeros(len(positions), dtype=np.uint64)
+        comps = np.zeros((len(positions), 2), dtype=np.uint8)
+        check(lib().bwtm_lf2(self._h, _p(positions, u64p), len(positions), _p(first, u64p), _p(second, u64p), _p(comps, u8p)))
+        return first, second, comps[:, 0], comps[:, 1]
 
     def count(self, patterns, char2comp=None):
         """Occurrences of each pattern (Range::length of FMI::find). patterns: list of uint8 arrays / bytes."""

@@ -297,7 +297,7 @@ struct PhaseClock   // BWTM_DEBUG=1: host wall clock per phase of the exchange, 
 };
 
 template<class KeyT>
-static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options,
                                   bwtm_index** result, bwtm_timings* timings)
 {
   NcclApi* api = nccl();
@@ -317,6 +317,9 @@ static int merge_distributed_impl(bwtm_comm* comm, const bwtm_index* a, const bw
   KeyT* sorted = nullptr;
   auto search_and_sort = [&]() -> int
   {
+    // Every rank walks 1/G of b's sequences but would build the pair records of all of a and b: the two-step walk is
+    // chosen as on one GPU, with the inserted share in place of |b|.
+    BWTM_TRY(prepare_walk(a, b, (uint64_t)((double)n_b * ((double)seq_count / (double)m_b)), stream, timings));
     timer.start();
     for(int attempt = 0; attempt < 2; attempt++)
     {

@@ -356,6 +356,8 @@ void index_free(bwtm_index* index)
   device_free(index->d_rle);
   device_free(index->d_records);
   device_free(index->d_super);
+  device_free(index->d_pairs);
+  device_free(index->d_pair_super);
   delete index;
 }
 

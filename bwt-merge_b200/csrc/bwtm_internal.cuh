@@ -20,6 +20,12 @@ struct bwtm_index
   uint64_t  counts[bwtm::SIGMA];
   uint64_t  C[bwtm::SIGMA + 1];
   uint64_t  device_bytes;
+  // Pair records for the two-step walk (bwtm_pairs.cu); built on first use as a merge input, may be absent.
+  uint4*    d_pairs;      // n_pair_records * 8
+  uint64_t  n_pair_records;
+  uint64_t* d_pair_super; // n_pair_super * 32
+  uint64_t  n_pair_super;
+  uint64_t  pair_bytes;
 };
 
 namespace bwtm
@@ -62,6 +68,11 @@ void index_free(bwtm_index* index);
 int index_from_planes(uint8_t* d_rle, uint64_t rle_bytes, uint4* d_records, uint64_t size, cudaStream_t stream, bwtm_index** out);
 // Fills the plane words of the records covering [first_position, first_position + count) from one-symbol-per-byte data.
 int planes_from_symbols(const uint8_t* d_symbols, uint64_t first_position, uint64_t count, uint4* d_records, cudaStream_t stream);
+
+// Pair records (bwtm_pairs.cu): two backward steps per record read.
+uint64_t pair_index_bytes(uint64_t size);
+int ensure_pair_index(bwtm_index* index, cudaStream_t stream);
+void release_pair_index(bwtm_index* index);
 
 // Per-64-byte-block symbol counts and their exclusive scan (block start positions).
 int rle_block_starts(const uint8_t* d_rle, uint64_t rle_bytes, uint64_t* d_starts /* blocks + 1 */, cudaStream_t stream);

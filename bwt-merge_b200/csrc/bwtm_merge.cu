@@ -1246,182 +1246,273 @@ int index_from_run_bytes(const uint8_t* d_runs, uint64_t n_runs, int layout, uin
   return index_from_filled_records(records, n, slab_symbols, stream, out);
 }
 
-// K1 and K2 overlapped. The walk is bound by random line requests and leaves most of the HBM bandwidth
-// idle; the radix sort is the opposite. B's sequences are walked in chunks on one stream (with a reduced
-// number of resident blocks per SM) while finished chunks are sorted and merged pairwise on a second
-// stream. The RA multiset does not depend on how B's sequences are split (fmi.cpp:355).
+//------------------------------------------------------------------------------
+// Search in batches (options.sequence_blocks): the counterpart of the reference's bounded buffers.
+//
+// The reference never holds the whole rank array as plain values: run buffers are sorted and compressed, merged
+// into thread buffers and merge buffers and spilled to disk (fmi.cpp:164-257, fmi.h:45-80), and mergeBWT streams
+// them back (support.h:576-638). On the device the array stays in HBM, but sorting it in one piece needs a second
+// buffer of the same size. With S > 1 the sequences of b are searched in S batches; every batch is sorted on its own
+// (the scratch buffer is batch-sized) and kept as a sorted run. The interleave then walks over ranges of A
+// positions: the pieces of the S runs that fall into a range are gathered, merged pairwise and consumed at once.
+// Peak memory: |b| keys + 2 batch-sized buffers instead of 2 |b| keys.
+
+// splitters[r] = smallest x with x + #{keys < x} >= r * step (r = 0: 0, r = ranges: n_a + 1);
+// bounds[r * S + k] = #{keys of run k below splitters[r]}.
 template<class KeyT>
-static int walk_sort_pipelined(const bwtm_index* a, const bwtm_index* b, KeyT* keys, KeyT* alt, uint64_t n_b, int bits, int chunks,
-                               KeyT** sorted, bwtm_timings* timings)
+__global__ void batch_splitters(const KeyT* __restrict__ keys, const unsigned long long* __restrict__ run_offsets, int S,
+                                unsigned long long n_a, unsigned long long step, unsigned long long ranges,
+                                unsigned long long* __restrict__ splitters, unsigned long long* __restrict__ bounds)
 {
-  const uint64_t m = b->sequences;
-  const uint64_t counter_stride = div_up(walk_counters_bytes(), 64) * 64;
-  int walk_blocks = 6;
-  if(const char* env = getenv("BWTM_WALK_CTAS")) { walk_blocks = atoi(env); }
-
-  DeviceBuffer counters, cursor, sort_temp, merge_temp;
-  BWTM_TRY(counters.allocate(counter_stride * chunks));
-  BWTM_TRY(cursor.allocate(sizeof(unsigned long long)));
-  BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, counter_stride * chunks, 0));
-  BWTM_CUDA(cudaMemsetAsync(cursor.ptr, 0, sizeof(unsigned long long), 0));
-  uint64_t max_chunk = std::min(n_b, (n_b / chunks) * 2 + (1 << 20));
-  size_t sort_bytes = 0, merge_bytes = 0;
+  unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if(r > ranges) { return; }
+  auto below = [&](unsigned long long x, int k) -> unsigned long long
   {
-    cub::DoubleBuffer<KeyT> probe(keys, alt);
-    BWTM_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, sort_bytes, probe, (int64_t)n_b, 0, bits, 0));
-    BWTM_CUDA(cub::DeviceMerge::MergeKeys(nullptr, merge_bytes, keys, (int)std::min<uint64_t>(n_b, 0x3FFFFFFF), keys, (int)std::min<uint64_t>(n_b, 0x3FFFFFFF), alt, ::cuda::std::less<>{}, 0));
-  }
-  (void)max_chunk;
-  BWTM_TRY(sort_temp.allocate(sort_bytes)); BWTM_TRY(merge_temp.allocate(merge_bytes));
-
-  std::vector<unsigned char> host_counters(counter_stride * chunks, 0);
-  std::vector<unsigned long long> host_cursor(chunks, 0);
-  unsigned long long* pinned = nullptr;
-  BWTM_CUDA(cudaMallocHost(&pinned, sizeof(unsigned long long) * chunks + counter_stride * chunks));
-  unsigned char* pinned_counters = reinterpret_cast<unsigned char*>(pinned + chunks);
-
-  cudaStream_t s_walk = nullptr, s_sort = nullptr;
-  cudaEvent_t ready = nullptr, begin = nullptr, walked_all = nullptr, done = nullptr;
-  std::vector<cudaEvent_t> walked(chunks, nullptr);
-  int rc = BWTM_OK;
-  auto cleanup = [&]()
-  {
-    if(s_walk) { cudaStreamSynchronize(s_walk); cudaStreamDestroy(s_walk); }
-    if(s_sort) { cudaStreamSynchronize(s_sort); cudaStreamDestroy(s_sort); }
-    for(cudaEvent_t e : walked) { if(e) { cudaEventDestroy(e); } }
-    for(cudaEvent_t e : { ready, begin, walked_all, done }) { if(e) { cudaEventDestroy(e); } }
-    if(pinned) { cudaFreeHost(pinned); }
+    unsigned long long lo = run_offsets[k], hi = run_offsets[k + 1];
+    while(lo < hi)
+    {
+      unsigned long long mid = lo + (hi - lo) / 2;
+      if((unsigned long long)keys[mid] < x) { lo = mid + 1; } else { hi = mid; }
+    }
+    return lo - run_offsets[k];
   };
-#define BWTM_PIPE(call) do { cudaError_t e__ = (call); if(e__ != cudaSuccess) { rc = cuda_failed(e__, #call, __FILE__, __LINE__); cleanup(); return rc; } } while(0)
-#define BWTM_PIPE_TRY(call) do { rc = (call); if(rc != BWTM_OK) { cleanup(); return rc; } } while(0)
-
-  BWTM_PIPE(cudaStreamCreateWithFlags(&s_walk, cudaStreamNonBlocking));
-  BWTM_PIPE(cudaStreamCreateWithFlags(&s_sort, cudaStreamNonBlocking));
-  BWTM_PIPE(cudaEventCreate(&ready)); BWTM_PIPE(cudaEventCreate(&begin));
-  BWTM_PIPE(cudaEventCreate(&walked_all)); BWTM_PIPE(cudaEventCreate(&done));
-  for(int c = 0; c < chunks; c++) { BWTM_PIPE(cudaEventCreateWithFlags(&walked[c], cudaEventDisableTiming)); }
-  BWTM_PIPE(cudaEventRecord(ready, 0));
-  BWTM_PIPE(cudaStreamWaitEvent(s_walk, ready, 0)); BWTM_PIPE(cudaStreamWaitEvent(s_sort, ready, 0));
-  BWTM_PIPE(cudaEventRecord(begin, s_walk));
-
-  // All walks are enqueued up front; each leaves its end offset and counters in pinned memory.
-  for(int c = 0; c < chunks; c++)
+  unsigned long long x = 0;
+  if(r == ranges) { x = n_a + 1; }
+  else if(r > 0)
   {
-    uint64_t first = (uint64_t)(((__uint128_t)m * c) / chunks), last = (uint64_t)(((__uint128_t)m * (c + 1)) / chunks);
-    if(last > first)
+    unsigned long long target = r * step, lo = 0, hi = n_a + 1;
+    while(lo < hi)
     {
-      BWTM_PIPE_TRY(walk_sequences_async<KeyT>(a, b, first, last - 1, keys, n_b, counters.as<unsigned char>() + counter_stride * c,
-                                               cursor.as<unsigned long long>(), walk_blocks, s_walk));
+      unsigned long long mid = lo + (hi - lo) / 2, placed = mid;
+      for(int k = 0; k < S; k++) { placed += below(mid, k); }
+      if(placed < target) { lo = mid + 1; } else { hi = mid; }
     }
-    BWTM_PIPE(cudaMemcpyAsync(pinned + c, cursor.ptr, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s_walk));
-    BWTM_PIPE(cudaMemcpyAsync(pinned_counters + counter_stride * c, counters.as<unsigned char>() + counter_stride * c, counter_stride,
-                              cudaMemcpyDeviceToHost, s_walk));
-    BWTM_PIPE(cudaEventRecord(walked[c], s_walk));
+    x = lo;
   }
-  BWTM_PIPE(cudaEventRecord(walked_all, s_walk));
-  timings->walk_kernel_launches = chunks;
+  splitters[r] = x;
+  for(int k = 0; k < S; k++) { bounds[r * S + k] = below(x, k); }
+}
 
-  // Sort every chunk as it arrives; merge equal-level neighbours (a binary counter of sorted runs).
-  struct SortedRun { uint64_t begin, end; int level; KeyT* where; };
-  std::vector<SortedRun> runs;
-  uint64_t previous_end = 0;
-  for(int c = 0; c < chunks; c++)
+// Merges the sorted pieces [offsets[k], offsets[k + 1]) of `src` pairwise, ping-ponging between two buffers.
+template<class KeyT>
+static int merge_pieces(KeyT* src, KeyT* dst, std::vector<uint64_t> offsets, cudaStream_t stream, DeviceBuffer& temp, KeyT** result)
+{
+  while(offsets.size() > 2)
   {
-    BWTM_PIPE(cudaEventSynchronize(walked[c]));
-    if(walk_counters_check(pinned_counters + counter_stride * c) || pinned[c] > n_b)
+    std::vector<uint64_t> next; next.push_back(0);
+    for(size_t k = 0; k + 1 < offsets.size(); k += 2)
     {
-      set_error("the rank array has more than %llu values: the inserted BWT is not a valid multi-string BWT", (unsigned long long)n_b);
-      rc = BWTM_ERR_INTERNAL; cleanup(); return rc;
-    }
-    uint64_t chunk_begin = previous_end, chunk_end = pinned[c];
-    previous_end = chunk_end;
-    if(chunk_end == chunk_begin) { continue; }
-    cub::DoubleBuffer<KeyT> buffers(keys + chunk_begin, alt + chunk_begin);
-    size_t bytes = sort_temp.bytes;
-    BWTM_PIPE(cub::DeviceRadixSort::SortKeys(sort_temp.ptr, bytes, buffers, (int64_t)(chunk_end - chunk_begin), 0, bits, s_sort));
-    count_launch((uint64_t)(2 + (bits + 7) / 8));
-    KeyT* base = (buffers.Current() == keys + chunk_begin ? keys : alt);
-    runs.push_back({ chunk_begin, chunk_end, 0, base });
-    while(runs.size() >= 2 && runs[runs.size() - 1].level == runs[runs.size() - 2].level)
-    {
-      SortedRun right = runs.back(); runs.pop_back();
-      SortedRun left = runs.back(); runs.pop_back();
-      KeyT* target = (left.where == keys ? alt : keys);
-      if(right.where != left.where)   // different pass parity cannot happen (same bit count), but stay safe
+      uint64_t begin = offsets[k], middle = offsets[k + 1], end = (k + 2 < offsets.size() ? offsets[k + 2] : offsets[k + 1]);
+      if(end == middle || middle == begin)
       {
-        BWTM_PIPE(cudaMemcpyAsync(left.where + right.begin, right.where + right.begin, (right.end - right.begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, s_sort));
+        if(end > begin) { BWTM_CUDA(cudaMemcpyAsync(dst + begin, src + begin, (end - begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream)); }
       }
-      size_t mb = merge_temp.bytes;
-      BWTM_PIPE(cub::DeviceMerge::MergeKeys(merge_temp.ptr, mb, left.where + left.begin, (int)(left.end - left.begin),
-                                            left.where + right.begin, (int)(right.end - right.begin), target + left.begin,
-                                            ::cuda::std::less<>{}, s_sort));
-      count_launch(2);
-      runs.push_back({ left.begin, right.end, left.level + 1, target });
+      else
+      {
+        size_t bytes = 0;
+        BWTM_CUDA(cub::DeviceMerge::MergeKeys(nullptr, bytes, src + begin, (int)(middle - begin), src + middle, (int)(end - middle), dst + begin, ::cuda::std::less<>{}, stream));
+        if(bytes > temp.bytes) { BWTM_CUDA(cudaStreamSynchronize(stream)); BWTM_TRY(temp.allocate(bytes)); }
+        BWTM_CUDA(cub::DeviceMerge::MergeKeys(temp.ptr, bytes, src + begin, (int)(middle - begin), src + middle, (int)(end - middle), dst + begin, ::cuda::std::less<>{}, stream));
+        count_launch(2);
+      }
+      next.push_back(end);
     }
+    offsets.swap(next);
+    std::swap(src, dst);
   }
-  // Leftover runs of different levels (chunk count not a power of two, or empty chunks): merge right to left.
-  while(runs.size() >= 2)
-  {
-    SortedRun right = runs.back(); runs.pop_back();
-    SortedRun left = runs.back(); runs.pop_back();
-    KeyT* target = (left.where == keys ? alt : keys);
-    if(right.where != left.where)
-    {
-      BWTM_PIPE(cudaMemcpyAsync(left.where + right.begin, right.where + right.begin, (right.end - right.begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, s_sort));
-    }
-    size_t mb = merge_temp.bytes;
-    BWTM_PIPE(cub::DeviceMerge::MergeKeys(merge_temp.ptr, mb, left.where + left.begin, (int)(left.end - left.begin),
-                                          left.where + right.begin, (int)(right.end - right.begin), target + left.begin,
-                                          ::cuda::std::less<>{}, s_sort));
-    count_launch(2);
-    runs.push_back({ left.begin, right.end, std::max(left.level, right.level) + 1, target });
-  }
-  BWTM_PIPE(cudaEventRecord(done, s_sort));
-  BWTM_PIPE(cudaEventSynchronize(done));
-  float walk_ms = 0.0f, total_ms = 0.0f;
-  cudaEventElapsedTime(&walk_ms, begin, walked_all);
-  cudaEventElapsedTime(&total_ms, begin, done);
-  timings->search_seconds = walk_ms * 1e-3;
-  timings->sort_seconds = std::max(0.0f, total_ms - walk_ms) * 1e-3;   // what the overlap did not hide
-  timings->ra_values = previous_end;
-  *sorted = (runs.empty() ? keys : runs.back().where);
-  uint64_t emitted = previous_end;
-  cleanup();
-#undef BWTM_PIPE
-#undef BWTM_PIPE_TRY
-  if(emitted != n_b)
-  {
-    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
-              (unsigned long long)emitted, (unsigned long long)n_b);
-    return BWTM_ERR_INTERNAL;
-  }
+  *result = src;
   return BWTM_OK;
 }
 
+// Memory the pool could hand out right now: free device memory plus what the pool holds but does not use.
+static uint64_t available_device_bytes()
+{
+  size_t free_bytes = 0, total_bytes = 0;
+  if(cudaMemGetInfo(&free_bytes, &total_bytes) != cudaSuccess) { cudaGetLastError(); return 0; }
+  uint64_t available = free_bytes;
+  int device = 0; cudaMemPool_t pool;
+  if(cudaGetDevice(&device) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess)
+  {
+    uint64_t reserved = 0, used = 0;
+    if(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+       cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) { available += reserved - used; }
+  }
+  cudaGetLastError();
+  return available;
+}
+
+// Number of search batches: options.sequence_blocks when given (> 0), else 1 unless two full key buffers would take
+// more than half of the memory that is available now.
+static uint64_t choose_batches(const bwtm_merge_options* options, uint64_t sequences, uint64_t n_b, uint64_t key_bytes)
+{
+  uint64_t batches = options->sequence_blocks;
+  if(const char* env = getenv("BWTM_SEQUENCE_BLOCKS")) { batches = strtoull(env, nullptr, 10); }
+  if(batches == 0)
+  {
+    batches = 1;
+    uint64_t available = available_device_bytes();
+    if(available > 0 && 2 * n_b * key_bytes > available / 2)
+    {
+      uint64_t batch_budget = std::max<uint64_t>(available / 16, 1ull << 28);   // two batch-sized buffers take an eighth
+      batches = div_up(n_b * key_bytes, batch_budget);
+    }
+  }
+  return std::max<uint64_t>(1, std::min(batches, sequences));
+}
+
 template<class KeyT>
-static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+static int merge_in_batches(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options, uint64_t batches,
+                            bwtm_index** result, bwtm_timings* timings)
+{
+  cudaStream_t stream = 0;
+  const uint64_t n_a = a->size, n_b = b->size, m = b->sequences;
+  const int S = (int)batches;
+  const int bits = bit_length_host(n_a);
+  EventTimer timer(stream);
+
+  // 1. search and sort, batch by batch: S sorted runs in `runs`
+  DeviceBuffer runs, scratch, counters;
+  BWTM_TRY(runs.allocate(n_b * sizeof(KeyT)));
+  BWTM_TRY(counters.allocate(walk_counters_bytes()));
+  std::vector<unsigned long long> run_offsets(S + 1, 0);
+  float search_ms = 0.0f, sort_ms = 0.0f;
+  for(int k = 0; k < S; k++)
+  {
+    uint64_t first = (uint64_t)(((__uint128_t)m * k) / S), last = (uint64_t)(((__uint128_t)m * (k + 1)) / S);
+    run_offsets[k + 1] = run_offsets[k];
+    if(last == first) { continue; }
+    uint64_t emitted = 0;
+    timer.start();
+    BWTM_TRY(walk_sequences<KeyT>(a, b, first, last - 1, runs.as<KeyT>() + run_offsets[k], n_b - run_offsets[k], &emitted, stream));
+    search_ms += timer.stop();
+    run_offsets[k + 1] = run_offsets[k] + emitted;
+    if(emitted == 0) { continue; }
+    timer.start();
+    if(emitted * sizeof(KeyT) > scratch.bytes) { BWTM_TRY(scratch.allocate(emitted * sizeof(KeyT) + (emitted * sizeof(KeyT) >> 3))); }
+    KeyT* sorted = nullptr;
+    BWTM_TRY(sort_keys<KeyT>(runs.as<KeyT>() + run_offsets[k], scratch.as<KeyT>(), emitted, bits, &sorted, stream, n_a + 1));
+    if(sorted != runs.as<KeyT>() + run_offsets[k])
+    {
+      BWTM_CUDA(cudaMemcpyAsync(runs.as<KeyT>() + run_offsets[k], sorted, emitted * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream));
+    }
+    sort_ms += timer.stop();
+  }
+  scratch.release();
+  timings->search_seconds = search_ms * 1e-3; timings->sort_seconds = sort_ms * 1e-3;
+  timings->walk_kernel_launches = S; timings->search_batches = S;
+  timings->ra_values = run_offsets[S];
+  if(run_offsets[S] != n_b)
+  {
+    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
+              (unsigned long long)run_offsets[S], (unsigned long long)n_b);
+    return BWTM_ERR_INTERNAL;
+  }
+
+  // 2. ranges of A positions holding about `step` merged positions each, and where they cut the runs
+  timer.start();
+  const uint64_t total = n_a + n_b;
+  const uint64_t step = clamp_slab(options->slab_symbols, total);
+  const uint64_t ranges = std::max<uint64_t>(1, div_up(total, step));
+  DeviceBuffer d_offsets, d_splitters, d_bounds;
+  BWTM_TRY(d_offsets.allocate((S + 1) * sizeof(unsigned long long)));
+  BWTM_TRY(d_splitters.allocate((ranges + 1) * sizeof(unsigned long long)));
+  BWTM_TRY(d_bounds.allocate((ranges + 1) * S * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemcpyAsync(d_offsets.ptr, run_offsets.data(), (S + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  batch_splitters<KeyT><<<(unsigned)div_up(ranges + 1, 64), 64, 0, stream>>>(runs.as<KeyT>(), d_offsets.as<unsigned long long>(), S, n_a, step, ranges,
+                                                                             d_splitters.as<unsigned long long>(), d_bounds.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  std::vector<unsigned long long> splitters(ranges + 1), bounds((ranges + 1) * S);
+  BWTM_CUDA(cudaMemcpyAsync(splitters.data(), d_splitters.ptr, (ranges + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.ptr, (ranges + 1) * S * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  uint64_t largest = 0;
+  std::vector<uint64_t> keys_before(ranges + 1, 0);
+  for(uint64_t r = 0; r <= ranges; r++)
+  {
+    for(int k = 0; k < S; k++) { keys_before[r] += bounds[r * S + k]; }
+    if(r > 0) { largest = std::max(largest, keys_before[r] - keys_before[r - 1]); }
+  }
+  DeviceBuffer gathered, merged_keys, merge_temp;
+  BWTM_TRY(gathered.allocate(std::max<uint64_t>(largest, 1) * sizeof(KeyT)));
+  BWTM_TRY(merged_keys.allocate(std::max<uint64_t>(largest, 1) * sizeof(KeyT)));
+  sort_ms = timer.stop();
+  timings->sort_seconds += sort_ms * 1e-3;
+
+  // 3. range by range: gather + merge the pieces, interleave, encode
+  DeviceBuffer distinct; BWTM_TRY(distinct.allocate(sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemsetAsync(distinct.ptr, 0, sizeof(unsigned long long), stream));
+  DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
+  BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream));
+  OutputBuffer out = { nullptr, 0, 0, nullptr };
+  int rc = ensure_capacity(&out, a->rle_bytes + b->rle_bytes + ((a->rle_bytes + b->rle_bytes) >> 2) + (1 << 20), 0, stream);
+  float interleave_ms = 0.0f, encode_ms = 0.0f, merge_ms = 0.0f;
+  for(uint64_t r = 0; rc == BWTM_OK && r < ranges; r++)
+  {
+    const uint64_t count = keys_before[r + 1] - keys_before[r];
+    const uint64_t begin = splitters[r] + keys_before[r];
+    const uint64_t end = (r + 1 == ranges ? total : splitters[r + 1] + keys_before[r + 1]);
+    const bool last = (r + 1 == ranges);
+    if(end == begin && !last) { continue; }
+    KeyT* range_keys = gathered.as<KeyT>();
+    timer.start();
+    std::vector<uint64_t> piece_offsets(1, 0);
+    for(int k = 0; rc == BWTM_OK && k < S; k++)
+    {
+      uint64_t from = run_offsets[k] + bounds[r * S + k], piece = bounds[(r + 1) * S + k] - bounds[r * S + k];
+      if(piece > 0 && cudaMemcpyAsync(gathered.as<KeyT>() + piece_offsets.back(), runs.as<KeyT>() + from, piece * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+      {
+        rc = cuda_failed(cudaGetLastError(), "gather of a run piece", __FILE__, __LINE__);
+      }
+      piece_offsets.push_back(piece_offsets.back() + piece);
+    }
+    if(rc == BWTM_OK) { rc = merge_pieces<KeyT>(gathered.as<KeyT>(), merged_keys.as<KeyT>(), piece_offsets, stream, merge_temp, &range_keys); }
+    merge_ms += timer.stop();
+    if(rc == BWTM_OK)
+    {
+      rc = interleave_range<KeyT>(a, b, range_keys, keys_before[r], count, begin, end, options->slab_symbols, &out, control.as<EncodeControl>(),
+                                  last, &interleave_ms, &encode_ms, stream, distinct.as<unsigned long long>(), nullptr);
+    }
+  }
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  timings->sort_seconds += merge_ms * 1e-3;
+  timings->interleave_seconds = interleave_ms * 1e-3; timings->encode_seconds = encode_ms * 1e-3;
+  runs.release(); gathered.release(); merged_keys.release();
+
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpy(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost));
+  unsigned long long ra_runs = 0;
+  BWTM_CUDA(cudaMemcpy(&ra_runs, distinct.ptr, sizeof(ra_runs), cudaMemcpyDeviceToHost));
+  timings->ra_runs = ra_runs; timings->merged_runs = ctl.runs_total; timings->merged_bytes = ctl.out_size;
+  if(options->host_output != nullptr)
+  {
+    if(options->host_output_capacity < ctl.out_size) { set_error("host_output is too small for %llu bytes", (unsigned long long)ctl.out_size); device_free(out.ptr); return BWTM_ERR_CAPACITY; }
+    BWTM_CUDA(cudaMemcpyAsync(options->host_output, out.ptr, ctl.out_size, cudaMemcpyDeviceToHost, stream));
+  }
+  timer.start();
+  uint64_t counts[SIGMA];
+  for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
+  rc = finish_index(&out, ctl.out_size, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
+  timings->index_seconds = timer.stop() * 1e-3;
+  device_free(out.ptr);
+  return rc;
+}
+
+template<class KeyT>
+static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options,
                       bwtm_index** result, bwtm_timings* timings)
 {
   cudaStream_t stream = 0;
   uint64_t n_b = b->size;
+  BWTM_TRY(prepare_walk(a, b, b->size, stream, timings));
+  const uint64_t batches = choose_batches(options, b->sequences, n_b, sizeof(KeyT));
+  if(batches > 1) { return merge_in_batches<KeyT>(a, b, options, batches, result, timings); }
+  timings->search_batches = 1;
   DeviceBuffer keys, alt;
   BWTM_TRY(keys.allocate(n_b * sizeof(KeyT)));
   BWTM_TRY(alt.allocate(n_b * sizeof(KeyT)));
 
   EventTimer timer(stream);
   KeyT* sorted = nullptr;
-  // Overlapping the walk with the sort of finished chunks is implemented (walk_sort_pipelined) but off by
-  // default: on B200 the two kernels slow each other down by as much as the overlap hides (config 2: 93 ms
-  // either way, profiles/r01_pipeline_sweep.txt). BWTM_PIPELINE_CHUNKS=<n> turns it on.
-  int chunks = 1;
-  if(const char* env = getenv("BWTM_PIPELINE_CHUNKS")) { chunks = atoi(env); }
-  uint64_t pipeline_min = 1ull << 26;   // below this the overlap does not pay for the extra launches
-  if(const char* env = getenv("BWTM_PIPELINE_MIN")) { pipeline_min = strtoull(env, nullptr, 10); }
-  if(chunks > 1 && n_b >= pipeline_min && n_b < 0x7FFFFFFFull && b->sequences >= (uint64_t)chunks)
-  {
-    BWTM_TRY(walk_sort_pipelined<KeyT>(a, b, keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), chunks, &sorted, timings));
-  }
-  else
   {
     timer.start();
     uint64_t emitted = 0;
@@ -1509,7 +1600,7 @@ static int merge_impl(const bwtm_index* a, const bwtm_index* b, const bwtm_merge
   return rc;
 }
 
-int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+int merge_local(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options,
                 bwtm_index** result, bwtm_timings* timings)
 {
   // BWTM_FORCE_WIDE=1 runs the 64-bit key and position paths on small inputs (tests).
@@ -1592,6 +1683,10 @@ int bwtm_rank_array(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first
   BWTM_TRY(keys.allocate(capacity * sizeof(uint64_t)));
   BWTM_TRY(alt.allocate(capacity * sizeof(uint64_t)));
   uint64_t emitted = 0;
+  {
+    bwtm_timings unused; std::memset(&unused, 0, sizeof(unused));   // same choice of walk as a merge of these inputs
+    BWTM_TRY(prepare_walk(const_cast<bwtm_index*>(a), const_cast<bwtm_index*>(b), b->size, 0, &unused));
+  }
   BWTM_TRY(walk_sequences<uint64_t>(a, b, seq_first, seq_last, keys.as<uint64_t>(), capacity, &emitted, 0));
   uint64_t* sorted = nullptr;
   BWTM_TRY(sort_keys<uint64_t>(keys.as<uint64_t>(), alt.as<uint64_t>(), emitted, bit_length_host(a->size), &sorted, 0, a->size + 1));

@@ -17,6 +17,15 @@ template<class KeyT>
 int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                          KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor,
                          int max_blocks_per_sm, cudaStream_t stream);
+// K1, two-step form (bwtm_pairs.cu): both indexes carry pair records.
+template<class KeyT>
+int walk_pairs_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                     KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, cudaStream_t stream);
+// Decides how b is walked against a and builds what that needs: pair records on both (two backward steps per
+// record read) when it pays for the `walked_bases` symbols of b this GPU searches and fits, else nothing (single-step walk on the basic records). Fills the walk_* fields
+// and pair_index_seconds of `timings`.
+int prepare_walk(bwtm_index* a, bwtm_index* b, uint64_t walked_bases, cudaStream_t stream, bwtm_timings* timings);
+bool walk_uses_pairs(const bwtm_index* a, const bwtm_index* b);
 uint64_t walk_counters_bytes();
 int walk_counters_check(const void* host_copy);   // non-zero: the output buffer overflowed
 
@@ -133,7 +142,7 @@ int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, 
                  cudaStream_t stream, bwtm_index** result, DeviceBuffer* filled_records = nullptr, uint64_t size = 0);
 int bit_length_host(uint64_t v);
 
-int merge_local(const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+int merge_local(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options,
                 bwtm_index** result, bwtm_timings* timings);
 
 // K4 for one slab: merged symbols of positions [p0, p1) as plane chunks, 16 bytes per 32 positions, chunk 0 at

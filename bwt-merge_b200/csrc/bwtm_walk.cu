@@ -9,11 +9,12 @@
 // starting from (a, b) = (sequences of A, sequence id) (fmi.cpp:286) and emits `a` for every suffix.
 // The emitted multiset equals the reference's RA after run expansion.
 //
-// One thread = one walker; a warp refills finished lanes from a global sequence counter, so lanes
-// stay busy for any mix of sequence lengths.  Every step is two dependent 64-byte record reads
-// (B then A) at unrelated addresses: the kernel is bound by HBM random-sector throughput and hides
-// the latency with occupancy (>= 1024 resident walkers per SM).  RA values are staged per warp in
-// shared memory and appended to the output in coalesced chunks claimed with one atomic per chunk.
+// Four lanes = one walker (k1_walk_coop below); a warp refills finished walkers from a global sequence
+// counter, so lanes stay busy for any mix of sequence lengths.  Every step is two 64-byte record reads
+// (B and A) at unrelated addresses: the kernel is bound by HBM random line requests and hides the latency
+// with occupancy.  RA values are staged per warp in shared memory and appended to the output in coalesced
+// chunks claimed with one atomic per chunk.  When both indexes carry pair records, the two-step form in
+// bwtm_pairs.cu (one 128-byte record per side and TWO steps) replaces it.
 #include <algorithm>
 #include <cstdlib>
 
@@ -35,106 +36,6 @@ struct WalkCounters
   unsigned long long emitted;         // output cursor (may be shared by consecutive launches: `cursor`)
   int                overflow;
 };
-
-template<class KeyT>
-__global__ void __launch_bounds__(WALK_THREADS, 4)
-k1_walk(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
-        KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor)
-{
-  __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
-  __shared__ uint64_t c_a[8], c_b[8];
-
-#pragma unroll
-  for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = a.C[c]; c_b[c] = b.C[c]; } }
-  __syncthreads();
-
-  const unsigned FULL = 0xFFFFFFFFu;
-  const int lane = threadIdx.x & 31;
-  const unsigned lanes_below = (1u << lane) - 1u;
-  KeyT* stage = stage_all[threadIdx.x >> 5];
-
-  uint32_t fill = 0;          // warp-uniform
-  bool exhausted = false;     // warp-uniform
-  bool alive = false;
-  uint64_t pos_a = 0, pos_b = 0;
-
-  while(true)
-  {
-    // Refill finished lanes with new sequences.
-    unsigned need = __ballot_sync(FULL, !alive);
-    if(need != 0 && !exhausted)
-    {
-      unsigned long long base = 0;
-      int wanted = __popc(need);
-      if(lane == 0) { base = atomicAdd(&(counters->next_sequence), (unsigned long long)wanted); }
-      base = __shfl_sync(FULL, base, 0);
-      uint64_t first = seq_begin + base;
-      if(!alive)
-      {
-        uint64_t mine = first + __popc(need & lanes_below);
-        if(mine < seq_end) { alive = true; pos_b = mine; pos_a = a.sequences; }
-      }
-      if(first + wanted >= seq_end) { exhausted = true; }
-    }
-
-    unsigned active = __ballot_sync(FULL, alive);
-    if(active == 0) { break; }
-
-    // Emit the rank of the current suffix (fmi.cpp:290 with a run of length 1).
-    if(alive) { stage[fill + __popc(active & lanes_below)] = (KeyT)pos_a; }
-    fill += __popc(active);
-    if(fill > WALK_STAGE - 32)
-    {
-      __syncwarp();
-      unsigned long long base = 0;
-      if(lane == 0) { base = atomicAdd(cursor, (unsigned long long)fill); }
-      base = __shfl_sync(FULL, base, 0);
-      if(base + fill <= capacity)
-      {
-        for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
-      }
-      else
-      {
-        // More values than |B|: the input is not a valid BWT (or the buffer is too small). Stop this warp.
-        if(lane == 0) { counters->overflow = 1; }
-        alive = false; exhausted = true;
-      }
-      __syncwarp();
-      fill = 0;
-    }
-
-    // One backward step.
-    if(alive)
-    {
-      uint64_t record = pos_b >> RECORD_SHIFT;
-      Record rb = load_record(b, record);
-      uint32_t offset = (uint32_t)(pos_b & (RECORD_SYMBOLS - 1));
-      uint32_t comp = record_symbol(rb, offset);
-      if(comp == 0) { alive = false; }
-      else
-      {
-        pos_b = c_b[comp] + record_base(b, rb, record, comp) + record_rank(rb, offset, comp);
-        uint64_t record_a = pos_a >> RECORD_SHIFT;
-        Record ra = load_record(a, record_a);
-        pos_a = c_a[comp] + record_base(a, ra, record_a, comp)
-              + record_rank(ra, (uint32_t)(pos_a & (RECORD_SYMBOLS - 1)), comp);
-      }
-    }
-  }
-
-  if(fill > 0)
-  {
-    __syncwarp();
-    unsigned long long base = 0;
-    if(lane == 0) { base = atomicAdd(cursor, (unsigned long long)fill); }
-    base = __shfl_sync(FULL, base, 0);
-    if(base + fill <= capacity)
-    {
-      for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
-    }
-    else if(lane == 0) { counters->overflow = 1; }
-  }
-}
 
 // K1, cooperative form.  Measured on B200 (profiles/r01_random_line_ceiling_coop_chase.txt): dependent random
 // reads are limited by the number of 128-byte LINE REQUESTS, about 39.4 G lines/s, whatever the record size
@@ -309,6 +210,10 @@ int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_
   int device = 0, sms = 0;
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+  if(walk_uses_pairs(a, b))   // two backward steps per record read (bwtm_pairs.cu)
+  {
+    return walk_pairs_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, stream);
+  }
   if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr)
   {
     BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream)));
@@ -339,25 +244,8 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
   DeviceBuffer counters; BWTM_TRY(counters.allocate(sizeof(WalkCounters)));
   BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, sizeof(WalkCounters), stream));
 
-  int device = 0, sms = 0, per_sm = 0;
-  BWTM_CUDA(cudaGetDevice(&device));
-  BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-  uint64_t sequences = seq_last + 1 - seq_first;
   unsigned long long* cursor = &(counters.as<WalkCounters>()->emitted);
-  const char* variant = getenv("BWTM_WALK");
-  if(variant != nullptr && variant[0] == '1')   // thread-per-walker form, kept for A/B measurements
-  {
-    BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk<KeyT>, WALK_THREADS, 0));
-    if(per_sm < 1) { per_sm = 1; }
-    uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS));
-    k1_walk<KeyT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
-      device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters.as<WalkCounters>(), cursor);
-    BWTM_LAUNCH_CHECK();
-  }
-  else
-  {
-    BWTM_TRY(walk_sequences_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters.ptr, cursor, 0, stream));
-  }
+  BWTM_TRY(walk_sequences_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters.ptr, cursor, 0, stream));
 
   WalkCounters host;
   BWTM_CUDA(cudaMemcpyAsync(&host, counters.ptr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, stream));

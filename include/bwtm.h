@@ -71,8 +71,12 @@ typedef struct
   uint64_t thread_buffer_size;     /* -b, ignored */
   uint64_t merge_buffers;          /* -m, ignored */
   uint64_t threads;                /* -t, ignored (the device schedules its own walkers) */
-  uint64_t sequence_blocks;        /* -s: >1 splits B's sequences into that many search batches (bounds
-                                      the rank-array buffer); 0 or 1 = one batch */
+  uint64_t sequence_blocks;        /* > 1: B's sequences are searched in that many batches, each sorted on its own and
+                                      kept as a sorted run; the interleave merges the runs range by range. Bounds the
+                                      work memory to |B| keys + two batch-sized buffers instead of 2 |B| keys (the
+                                      counterpart of the reference's run/thread/merge buffers, fmi.cpp:164-257).
+                                      1 = one batch; 0 = chosen from the free device memory. NOT the reference's -s,
+                                      which counts CPU work units (4 per thread by default). */
   const char* temp_dir;            /* -d, ignored */
   /* device-side knobs (0 = default) */
   uint64_t slab_symbols;           /* merged positions interleaved per pass (default 2^30) */
@@ -102,6 +106,13 @@ typedef struct
   uint64_t merged_bytes;           /* RLE bytes of the merged BWT */
   uint64_t walk_kernel_launches;
   uint64_t kernel_launches;        /* all kernels launched by this library during the merge */
+  /* How the search read the indexes: 64-byte records answer one backward step (two record reads per inserted
+     base), 128-byte pair records answer two (one read per base). Pair records are built on first use of an index
+     as a merge input and stay with it; the time spent building them inside this merge is pair_index_seconds. */
+  double   pair_index_seconds;
+  uint64_t walk_record_bytes;
+  uint64_t walk_table_bytes;       /* bytes of the structures the walk reads at random (both indexes) */
+  uint64_t search_batches;         /* batches B's sequences were searched in (options.sequence_blocks) */
 } bwtm_timings;
 
 /*----------------------------------------------------------------------------*/
@@ -169,6 +180,17 @@ int bwtm_lf(const bwtm_index* index, const uint64_t* positions, uint64_t n,
    comp values. This is the per-pattern value verifyFMI adds to `results` (bwt_merge.cpp:253-254). */
 int bwtm_count(const bwtm_index* index, const uint8_t* patterns, const uint64_t* offsets, uint64_t n,
                const uint8_t* char2comp, uint64_t* out_counts);
+
+/* Builds the pair records of an index now (2 bytes per symbol on top of the basic rank records) instead of on its
+   first use as a merge input; a no-op when they exist. bwtm_merge builds them itself when the inserted collection is
+   large enough to pay for it; a caller that merges the same index repeatedly, or distributes a merge over several
+   GPUs (where every rank would build them for 1/G of the search), can do it once up front. */
+int bwtm_index_build_pairs(bwtm_index* index);
+/* Two backward steps at once, from the pair records (built on first use): for every position i, comps[2k] =
+   BWT[i], comps[2k+1] = BWT[LF(i)], first = LF(i), second = LF(LF(i)) (0 where the step starts at an endmarker).
+   Equals two applications of bwtm_lf; the rank-array search uses it to read one record per two inserted bases. */
+int bwtm_lf2(bwtm_index* index, const uint64_t* positions, uint64_t n,
+             uint64_t* out_first, uint64_t* out_second, uint8_t* out_comps);
 
 /*----------------------------------------------------------------------------*/
 /* Merge: replaces FMI::FMI(FMI& a, FMI& b, MergeParameters) (fmi.cpp:336-369):

@@ -33,7 +33,7 @@ def test_version_and_error_string(library):
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(bwtm_b200.IndexInfo) == 8 * (3 + 6 + 7 + 1)
     assert ctypes.sizeof(bwtm_b200.MergeOptions) == 8 * 6 + 8 + 4 + 4 + 8 + 8
-    assert ctypes.sizeof(bwtm_b200.Timings) == 8 * 13
+    assert ctypes.sizeof(bwtm_b200.Timings) == 8 * 17
 
 
 def test_no_cpu_fallback(library):

@@ -275,22 +275,110 @@ def test_invalid_inputs_fail_loudly(oracle):
         FMI.merge(FMI.from_rle(A.rle()), FMI.from_comps(bogus))
 
 
-@pytest.mark.parametrize("chunks", [2, 3, 4, 7])
-def test_pipelined_walk_and_sort(oracle, monkeypatch, chunks):
-    """The chunked walk overlapped with sort + pairwise merges (used for large inputs), forced on small ones."""
-    monkeypatch.setenv("BWTM_PIPELINE_MIN", "1")
-    monkeypatch.setenv("BWTM_PIPELINE_CHUNKS", str(chunks))
-    for shape in ("reads", "noisy_N", "repeats"):
+@pytest.mark.parametrize("slab", [0, 4096])
+@pytest.mark.parametrize("batches", [2, 3, 5, 7])
+def test_search_in_batches(oracle, batches, slab):
+    """options.sequence_blocks > 1 (the counterpart of the reference's bounded buffers, fmi.cpp:164-257): b's sequences
+    are searched in batches kept as sorted runs, and the interleave gathers and merges the pieces of every range of A
+    positions. Same bytes as the one-shot merge, including the reference's RA run count."""
+    for shape in ("reads", "noisy_N", "repeats", "single"):
         ra, bwt_a, rb, bwt_b = collections(oracle, shape)
         A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
-        M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()))
-        assert np.array_equal(M.rle(), oracle.merge(A, B).rle()), (shape, chunks)
-        assert M.timings.walk_kernel_launches == chunks
+        p = MergeParameters(); p.sequence_blocks = batches; p.slab_symbols = slab
+        M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+        want = oracle.merge(A, B)
+        assert np.array_equal(M.rle(), want.rle()), (shape, batches)
+        assert M.timings.search_batches == min(batches, B.sequences)
+        assert M.timings.ra_runs == len(oracle.sort_compress(oracle.build_ra_dfs(A, B)))
+        assert M.hash() == want.hash()
     rng = np.random.default_rng(9)
     g = synth.genome(2000, 42)
     ra = _variable_reads(rng, g, 200, 1, 300); rb = _variable_reads(rng, g, 150, 1, 300)
     A, B = oracle.from_comps(oracle.bwt_of_reads(ra)), oracle.from_comps(oracle.bwt_of_reads(rb))
+    p = MergeParameters(); p.sequence_blocks = batches; p.slab_symbols = slab
+    out = np.zeros(A.bytes + B.bytes + 4096, dtype=np.uint8); p.host_output = out
+    M = FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle()), p)
+    want = oracle.merge(A, B).rle()
+    assert np.array_equal(M.rle(), want) and np.array_equal(out[:len(want)], want)
+
+
+@pytest.mark.parametrize("shape", list(SHAPES))
+def test_pair_records_answer_two_steps(oracle, shape):
+    """bwtm_lf2 (the pair records of bwtm_pairs.cu) equals two applications of FMI::LF(i) (fmi.h:147-150), and both
+    equal the reference's inverse_select restated in the oracle."""
+    ra, bwt_a, rb, bwt_b = collections(oracle, shape)
+    A = oracle.from_comps(bwt_a)
+    D = FMI.from_rle(A.rle())
+    n = A.size
+    pos = np.arange(n, dtype=np.uint64) if n <= 40000 else np.random.default_rng(5).integers(0, n, 40000).astype(np.uint64)
+    first, second, c1, c2 = D.LF2(pos)
+    one, comp1 = D.LF(pos)
+    assert np.array_equal(c1, comp1)
+    live = comp1 != 0
+    assert np.array_equal(first[live], one[live]) and not first[~live].any() and not second[~live].any() and not c2[~live].any()
+    two, comp2 = D.LF(one[live])
+    assert np.array_equal(c2[live], comp2)
+    live2 = comp2 != 0
+    assert np.array_equal(second[live][live2], two[live2]) and not second[live][~live2].any()
+    C_ = A.C()
+    for i in pos[:300]:
+        r, c = A.inverse_select(int(i))
+        k = int(np.nonzero(pos == i)[0][0])
+        assert c == c1[k] and (c == 0 or first[k] == C_[c] + r)
+
+
+@pytest.mark.parametrize("walk", ["single", "pairs"])
+@pytest.mark.parametrize("wide", [False, True])
+def test_both_walks_give_the_reference_rank_array(oracle, monkeypatch, walk, wide):
+    """The single-step walk (64-byte records) and the two-step walk (128-byte pair records) emit the multiset that
+    buildRA (fmi.cpp:272-334) emits, with 32- and 64-bit positions, and merges through either are byte-identical."""
+    monkeypatch.setenv("BWTM_WALK", walk)
+    if wide:
+        monkeypatch.setenv("BWTM_FORCE_WIDE", "1")
+    for shape in SHAPES:
+        ra, bwt_a, rb, bwt_b = collections(oracle, shape)
+        A, B = oracle.from_comps(bwt_a), oracle.from_comps(bwt_b)
+        DA, DB = FMI.from_rle(A.rle()), FMI.from_rle(B.rle())
+        runs = oracle.build_ra_dfs(A, B)
+        want = np.sort(np.repeat(runs[:, 0], runs[:, 1].astype(np.int64)))
+        assert np.array_equal(bwtm_b200.rank_array(DA, DB), want), (shape, walk)
+        M = FMI.merge(DA, DB)
+        assert M.timings.walk_record_bytes == (128 if walk == "pairs" else 64)
+        assert np.array_equal(M.rle(), oracle.merge(A, B).rle()), (shape, walk)
+    # sequences of odd and even lengths, length 0 included: the two-step walk stops after either step
+    rng = np.random.default_rng(21)
+    g = synth.genome(1500, 42)
+    ra = _variable_reads(rng, g, 120, 1, 90); rb = _variable_reads(rng, g, 200, 1, 7)
+    A, B = oracle.from_comps(oracle.bwt_of_reads(ra)), oracle.from_comps(oracle.bwt_of_reads(rb))
     assert np.array_equal(FMI.merge(FMI.from_rle(A.rle()), FMI.from_rle(B.rle())).rle(), oracle.merge(A, B).rle())
+
+
+def test_pair_records_across_superblocks():
+    """More than 2^20 positions (pair superblocks) and a sequential merge whose inputs keep or lack pair records."""
+    thr = synth.error_threshold(0.02)
+    A = FMI.synthetic(300_000, 42, 100, thr, [(1, 30_000)])      # 3.03 M symbols: three pair superblocks
+    B = FMI.synthetic(300_000, 42, 100, thr, [(2, 20_000)])
+    pos = np.random.default_rng(2).integers(0, A.size(), 50_000).astype(np.uint64)
+    first, second, c1, c2 = A.LF2(pos)
+    one, comp1 = A.LF(pos)
+    live = comp1 != 0
+    two, comp2 = A.LF(one[live])
+    assert np.array_equal(c1, comp1) and np.array_equal(first[live], one[live]) and np.array_equal(c2[live], comp2)
+    assert np.array_equal(second[live][comp2 != 0], two[comp2 != 0])
+    os.environ["BWTM_WALK"] = "single"
+    try:
+        want = FMI.merge(A, B, keep_inputs=True).rle()
+    finally:
+        del os.environ["BWTM_WALK"]
+    os.environ["BWTM_WALK"] = "pairs"
+    try:
+        got = FMI.merge(A, B, keep_inputs=True)
+        assert got.timings.walk_record_bytes == 128
+    finally:
+        del os.environ["BWTM_WALK"]
+    assert np.array_equal(got.rle(), want)
+    direct = FMI.synthetic(300_000, 42, 100, thr, [(1, 30_000), (2, 20_000)])
+    assert np.array_equal(direct.rle(), want)
 
 
 @pytest.mark.parametrize("slab", [0, 4096])
