@@ -43,6 +43,21 @@ int cuda_failed(cudaError_t err, const char* what, const char* file, int line)
 
 void count_launch(uint64_t n) { launch_counter()->fetch_add(n); }
 
+// Total memory of the current device, asked once per device (cudaMemGetInfo takes milliseconds).
+uint64_t device_total_bytes()
+{
+  static uint64_t totals[64] = { 0 };
+  int device = 0;
+  if(cudaGetDevice(&device) != cudaSuccess || device < 0 || device >= 64) { cudaGetLastError(); return 0; }
+  if(totals[device] == 0)
+  {
+    size_t free_bytes = 0, total_bytes = 0;
+    if(cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess) { totals[device] = total_bytes; }
+    cudaGetLastError();
+  }
+  return totals[device];
+}
+
 // All device memory comes from the device's default stream-ordered pool with an unlimited release
 // threshold: buffers freed by one merge are reused by the next one instead of going back to the driver
 // (cudaMalloc/cudaFree of the multi-GB work buffers cost more than the kernels they serve).

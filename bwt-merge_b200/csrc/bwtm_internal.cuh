@@ -42,6 +42,8 @@ inline DeviceIndex device_view(const bwtm_index* index)
   return v;
 }
 
+uint64_t device_total_bytes();   // of the current device, cached
+
 // Stream-ordered pool allocation (bwtm_index.cu).
 int device_alloc(void** ptr, uint64_t bytes);
 void device_free(void* ptr);

@@ -1325,6 +1325,7 @@ static int merge_pieces(KeyT* src, KeyT* dst, std::vector<uint64_t> offsets, cud
 }
 
 // Memory the pool could hand out right now: free device memory plus what the pool holds but does not use.
+// cudaMemGetInfo costs milliseconds: only called when the answer can matter (see choose_batches).
 static uint64_t available_device_bytes()
 {
   size_t free_bytes = 0, total_bytes = 0;
@@ -1342,7 +1343,8 @@ static uint64_t available_device_bytes()
 }
 
 // Number of search batches: options.sequence_blocks when given (> 0), else 1 unless two full key buffers would take
-// more than half of the memory that is available now.
+// more than half of the memory that is available now (only looked at when they take more than an eighth of the
+// device's memory: small merges never pay for the query).
 static uint64_t choose_batches(const bwtm_merge_options* options, uint64_t sequences, uint64_t n_b, uint64_t key_bytes)
 {
   uint64_t batches = options->sequence_blocks;
@@ -1350,11 +1352,14 @@ static uint64_t choose_batches(const bwtm_merge_options* options, uint64_t seque
   if(batches == 0)
   {
     batches = 1;
-    uint64_t available = available_device_bytes();
-    if(available > 0 && 2 * n_b * key_bytes > available / 2)
+    if(2 * n_b * key_bytes > device_total_bytes() / 8)
     {
-      uint64_t batch_budget = std::max<uint64_t>(available / 16, 1ull << 28);   // two batch-sized buffers take an eighth
-      batches = div_up(n_b * key_bytes, batch_budget);
+      uint64_t available = available_device_bytes();
+      if(available > 0 && 2 * n_b * key_bytes > available / 2)
+      {
+        uint64_t batch_budget = std::max<uint64_t>(available / 16, 1ull << 28);   // two batch-sized buffers take an eighth
+        batches = div_up(n_b * key_bytes, batch_budget);
+      }
     }
   }
   return std::max<uint64_t>(1, std::min(batches, sequences));

@@ -44,7 +44,37 @@ constexpr uint32_t PAIR_FIELD_MASK = (1u << 20) - 1;
 //------------------------------------------------------------------------------
 // Builder
 
-// One thread per 32-position chunk of the basic records: c2 planes by following LF, c1 planes copied.
+// Bit deposit ("expand", the inverse of compress; Hacker's Delight 7-5): the low popc(mask) bits of x go to the set
+// positions of mask, in order. The five move masks depend on the mask only and serve all three bit planes.
+struct DepositNetwork { uint32_t move[5]; uint32_t mask; };
+
+__device__ __forceinline__ DepositNetwork deposit_network(uint32_t m)
+{
+  DepositNetwork net; net.mask = m;
+  uint32_t mk = ~m << 1;
+#pragma unroll
+  for(int i = 0; i < 5; i++)
+  {
+    uint32_t mp = mk ^ (mk << 1); mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+    uint32_t mv = mp & m;
+    net.move[i] = mv;
+    m = (m ^ mv) | (mv >> (1u << i));
+    mk &= ~mp;
+  }
+  return net;
+}
+
+__device__ __forceinline__ uint32_t deposit(const DepositNetwork& net, uint32_t x)
+{
+#pragma unroll
+  for(int i = 4; i >= 0; i--) { uint32_t mv = net.move[i]; x = (x & ~mv) | ((x << (1u << i)) & mv); }
+  return x & net.mask;
+}
+
+// One thread per 32-position chunk of the basic records: c1 planes copied, c2 planes by following LF. For a symbol
+// c the occurrences in the chunk map to CONSECUTIVE positions j, j + 1, ... (LF is order-preserving per symbol), so
+// their c2 values are a window of up to 32 bits of each plane starting at j, and a bit deposit puts them at the
+// chunk positions that hold c. No loop over occurrences: every thread does the same work.
 __global__ void __launch_bounds__(256)
 pairs_gather(DeviceIndex idx, uint64_t n_chunks, uint32_t* __restrict__ pair_words)
 {
@@ -68,35 +98,31 @@ pairs_gather(DeviceIndex idx, uint64_t n_chunks, uint32_t* __restrict__ pair_wor
     other = __shfl_up_sync(FULL, before, 2, 4);          if(sub >= 2) { before += other; }
   }
   before -= packed;
+  if(chunk >= n_chunks) { return; }
 
-  const uint64_t record = chunk >> 2;
-  const uint64_t* super_row = idx.super + (record >> SUPER_RECORD_SHIFT) * SUPER_STRIDE;
+  const uint64_t* super_row = idx.super + ((chunk >> 2) >> SUPER_RECORD_SHIFT) * SUPER_STRIDE;
   uint32_t t0 = 0, t1 = 0, t2 = 0;
-  uint64_t cached = ~0ull; uint4 target = make_uint4(0, 0, 0, 0);
-  if(chunk < n_chunks)
-  {
 #pragma unroll
-    for(uint32_t c = 1; c < SIGMA; c++)
-    {
-      uint32_t m = match_mask(q, c);
-      if(m == 0) { continue; }
-      uint64_t j = idx.C[c] + __ldg(super_row + c) + header_field(h0, h1, h2, h3, c) + ((before >> (8 * (c - 1))) & 0xFFu);
-      while(m != 0)
-      {
-        uint32_t t = __ffs(m) - 1; m &= m - 1;
-        if((j >> 5) != cached) { cached = j >> 5; target = __ldg(idx.records + cached); }
-        uint32_t bit = (uint32_t)j & 31u;
-        t0 |= ((target.x >> bit) & 1u) << t; t1 |= ((target.y >> bit) & 1u) << t; t2 |= ((target.z >> bit) & 1u) << t;
-        j++;
-      }
-    }
-    uint32_t* words = pair_words + (chunk >> 1) * PAIR_WORDS + (chunk & 1) * 8;
-    *reinterpret_cast<uint4*>(words) = make_uint4(q.x, q.y, q.z, t0);
-    *reinterpret_cast<uint2*>(words + 4) = make_uint2(t1, t2);
+  for(uint32_t c = 1; c < SIGMA; c++)
+  {
+    const uint32_t m = match_mask(q, c);
+    if(m == 0) { continue; }
+    const uint64_t j = idx.C[c] + __ldg(super_row + c) + header_field(h0, h1, h2, h3, c) + ((before >> (8 * (c - 1))) & 0xFFu);
+    const uint32_t shift = (uint32_t)j & 31u;
+    const uint4 lo = __ldg(idx.records + (j >> 5));
+    uint4 hi = make_uint4(0, 0, 0, 0);
+    if(shift + __popc(m) > 32) { hi = __ldg(idx.records + (j >> 5) + 1); }
+    const DepositNetwork net = deposit_network(m);
+    t0 |= deposit(net, __funnelshift_r(lo.x, hi.x, shift));
+    t1 |= deposit(net, __funnelshift_r(lo.y, hi.y, shift));
+    t2 |= deposit(net, __funnelshift_r(lo.z, hi.z, shift));
   }
+  uint32_t* words = pair_words + (chunk >> 1) * PAIR_WORDS + (chunk & 1) * 8;
+  *reinterpret_cast<uint4*>(words) = make_uint4(q.x, q.y, q.z, t0);
+  *reinterpret_cast<uint2*>(words + 4) = make_uint2(t1, t2);
 }
 
-// The 25 pair counts of one pair record (both halves).
+// The 25 pair counts of one pair record (both halves), added to counts[].
 __device__ __forceinline__ void pair_record_counts(const uint32_t* __restrict__ words, uint32_t counts[25])
 {
 #pragma unroll
@@ -118,34 +144,114 @@ __device__ __forceinline__ void pair_record_counts(const uint32_t* __restrict__ 
   }
 }
 
-constexpr int PAIR_FILL_THREADS = 1024;
-constexpr int PAIR_RECORDS_PER_THREAD = PAIR_RECORDS_PER_SUPER / PAIR_FILL_THREADS;   // 16
+constexpr int PAIR_FILL_THREADS = 512;
+constexpr int PAIR_FILL_WARPS   = PAIR_FILL_THREADS / 32;                           // 16
+constexpr int PAIR_FILL_ROUNDS  = PAIR_RECORDS_PER_SUPER / PAIR_FILL_THREADS;       // 32 rounds of 32 records per warp
 
-// Totals of every pair superblock: totals[sb * 25 + k].
+// Counters of every pair record, one CTA per pair superblock: the 25 pair counters relative to the superblock, the
+// five single counters (relative to the 2^25 superblock) from the header of the basic record, and the superblock's
+// totals for the table. Warp w owns the records [1024 w, 1024 w + 1024) of the superblock; in a round its lanes take
+// 32 consecutive records, so that loads and stores of a round cover 4 KB of contiguous memory. Two phases: totals of
+// the warps first (their exclusive scan gives every warp its base), then the same counts again, scanned over the
+// lanes of every round (two 16-bit classes per word), packed and stored.
 __global__ void __launch_bounds__(PAIR_FILL_THREADS)
-pairs_count(const uint32_t* __restrict__ pair_words, uint64_t n_pair_records, unsigned long long* __restrict__ totals)
+pairs_fill(DeviceIndex idx, uint32_t* __restrict__ pair_words, uint64_t n_pair_records, unsigned long long* __restrict__ totals)
 {
-  __shared__ unsigned int sums[25];
-  if(threadIdx.x < 25) { sums[threadIdx.x] = 0; }
-  __syncthreads();
-  uint32_t counts[25];
+  __shared__ uint32_t warp_totals[25][PAIR_FILL_WARPS];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint64_t warp_first = (uint64_t)blockIdx.x * PAIR_RECORDS_PER_SUPER + (uint64_t)warp * (32 * PAIR_FILL_ROUNDS);
+
+  uint32_t base[25];
 #pragma unroll
-  for(int k = 0; k < 25; k++) { counts[k] = 0; }
-  uint64_t first = (uint64_t)blockIdx.x * PAIR_RECORDS_PER_SUPER + (uint64_t)threadIdx.x * PAIR_RECORDS_PER_THREAD;
-  for(int r = 0; r < PAIR_RECORDS_PER_THREAD; r++)
+  for(int k = 0; k < 25; k++) { base[k] = 0; }
+  for(int round = 0; round < PAIR_FILL_ROUNDS; round++)
   {
-    if(first + r < n_pair_records) { pair_record_counts(pair_words + (first + r) * PAIR_WORDS, counts); }
+    uint64_t record = warp_first + 32 * round + lane;
+    if(record < n_pair_records) { pair_record_counts(pair_words + record * PAIR_WORDS, base); }
   }
 #pragma unroll
   for(int k = 0; k < 25; k++)
   {
-    uint32_t v = counts[k];
+    uint32_t v = base[k];
 #pragma unroll
     for(int offset = 16; offset > 0; offset >>= 1) { v += __shfl_xor_sync(0xFFFFFFFFu, v, offset); }
-    if((threadIdx.x & 31) == 0 && v != 0) { atomicAdd(&sums[k], v); }
+    if(lane == 0) { warp_totals[k][warp] = v; }
   }
   __syncthreads();
-  if(threadIdx.x < 25) { totals[(uint64_t)blockIdx.x * 25 + threadIdx.x] = sums[threadIdx.x]; }
+  if(threadIdx.x < 25)   // exclusive scan over the warps, class by class; the superblock's total goes to the table builder
+  {
+    uint32_t running = 0;
+    for(int w = 0; w < PAIR_FILL_WARPS; w++) { uint32_t v = warp_totals[threadIdx.x][w]; warp_totals[threadIdx.x][w] = running; running += v; }
+    totals[(uint64_t)blockIdx.x * 25 + threadIdx.x] = running;
+  }
+  __syncthreads();
+#pragma unroll
+  for(int k = 0; k < 25; k++) { base[k] = warp_totals[k][warp]; }
+
+  for(int round = 0; round < PAIR_FILL_ROUNDS; round++)
+  {
+    const uint64_t record = warp_first + 32 * round + lane;
+    const bool valid = (record < n_pair_records);
+    uint32_t* words = pair_words + record * PAIR_WORDS;
+    uint32_t counts[25];
+#pragma unroll
+    for(int k = 0; k < 25; k++) { counts[k] = 0; }
+    if(valid) { pair_record_counts(words, counts); }
+    // inclusive scan over the lanes, two classes per word (a round holds at most 32 * 64 = 2048 of a class)
+    uint32_t scanned[13];
+#pragma unroll
+    for(int i = 0; i < 13; i++) { scanned[i] = counts[2 * i] | (i < 12 ? counts[2 * i + 1] << 16 : 0u); }
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+#pragma unroll
+      for(int i = 0; i < 13; i++)
+      {
+        uint32_t other = __shfl_up_sync(0xFFFFFFFFu, scanned[i], offset);
+        if(lane >= (uint32_t)offset) { scanned[i] += other; }
+      }
+    }
+    if(valid)
+    {
+      // 25 x 20 bits -> words 16..31
+      uint32_t out[16];
+      uint64_t accumulator = 0; int bits = 0, word = 0;
+#pragma unroll
+      for(int k = 0; k < 25; k++)
+      {
+        uint32_t inclusive = (k & 1 ? scanned[k >> 1] >> 16 : scanned[k >> 1] & 0xFFFFu);
+        uint32_t prefix = base[k] + inclusive - counts[k];
+        accumulator |= (uint64_t)(prefix & PAIR_FIELD_MASK) << bits; bits += 20;
+        if(bits >= 32) { out[word++] = (uint32_t)accumulator; accumulator >>= 32; bits -= 32; }
+      }
+      out[word] = (uint32_t)accumulator;   // bits 480..499 end in word 15
+      uint4* destination = reinterpret_cast<uint4*>(words + 16);
+      destination[0] = make_uint4(out[0], out[1], out[2], out[3]);    destination[1] = make_uint4(out[4], out[5], out[6], out[7]);
+      destination[2] = make_uint4(out[8], out[9], out[10], out[11]);  destination[3] = make_uint4(out[12], out[13], out[14], out[15]);
+      // single counters: header of the basic record (+ its first half for the odd pair record)
+      const uint4* basic = idx.records + 4 * (record >> 1);
+      uint4 q0 = __ldg(basic), q1 = __ldg(basic + 1), q2 = __ldg(basic + 2), q3 = __ldg(basic + 3);
+      uint64_t field[SIGMA];
+#pragma unroll
+      for(uint32_t c = 1; c < SIGMA; c++)
+      {
+        field[c] = header_field(q0.w, q1.w, q2.w, q3.w, c);
+        if(record & 1) { field[c] += __popc(match_mask(q0, c)) + __popc(match_mask(q1, c)); }
+      }
+      uint64_t lo = field[1] | (field[2] << 25) | (field[3] << 50);
+      uint64_t hi = (field[3] >> 14) | (field[4] << 11) | (field[5] << 36);
+      *reinterpret_cast<uint2*>(words + 6) = make_uint2((uint32_t)lo, (uint32_t)(lo >> 32));
+      *reinterpret_cast<uint2*>(words + 14) = make_uint2((uint32_t)hi, (uint32_t)(hi >> 32));
+    }
+    // the round's totals (lane 31 holds them) move the warp's base
+#pragma unroll
+    for(int i = 0; i < 13; i++)
+    {
+      uint32_t total = __shfl_sync(0xFFFFFFFFu, scanned[i], 31);
+      base[2 * i] += total & 0xFFFFu;
+      if(i < 12) { base[2 * i + 1] += total >> 16; }
+    }
+  }
 }
 
 // One block: the superblock table (32 u64 per row). Thread k < 25 scans its pair class over the superblocks and
@@ -165,85 +271,6 @@ __global__ void pairs_super(DeviceIndex idx, const unsigned long long* __restric
   {
     super2[sb * PAIR_SUPER_STRIDE + k] = running;
     running += totals[sb * 25 + k];
-  }
-}
-
-// Counters of every pair record: the 25 pair counters relative to the pair superblock (one CTA per superblock)
-// and the five single counters relative to the 2^25 superblock, taken from the header of the basic record.
-__global__ void __launch_bounds__(PAIR_FILL_THREADS)
-pairs_fill(DeviceIndex idx, uint32_t* __restrict__ pair_words, uint64_t n_pair_records)
-{
-  __shared__ uint32_t warp_sums[25][PAIR_FILL_THREADS / 32];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint64_t first = (uint64_t)blockIdx.x * PAIR_RECORDS_PER_SUPER + (uint64_t)threadIdx.x * PAIR_RECORDS_PER_THREAD;
-
-  uint32_t running[25];
-#pragma unroll
-  for(int k = 0; k < 25; k++) { running[k] = 0; }
-  for(int r = 0; r < PAIR_RECORDS_PER_THREAD; r++)
-  {
-    if(first + r < n_pair_records) { pair_record_counts(pair_words + (first + r) * PAIR_WORDS, running); }
-  }
-  // Exclusive scan of the per-thread totals over the CTA, class by class.
-#pragma unroll
-  for(int k = 0; k < 25; k++)
-  {
-    uint32_t inclusive = running[k];
-#pragma unroll
-    for(int offset = 1; offset < 32; offset <<= 1)
-    {
-      uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-      if(lane >= (uint32_t)offset) { inclusive += other; }
-    }
-    if(lane == 31) { warp_sums[k][warp] = inclusive; }
-    running[k] = inclusive - running[k];   // exclusive within the warp
-  }
-  __syncthreads();
-  if(warp < 25)   // warp k scans the warp totals of class k
-  {
-    uint32_t value = warp_sums[warp][lane], inclusive = value;
-#pragma unroll
-    for(int offset = 1; offset < 32; offset <<= 1)
-    {
-      uint32_t other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
-      if(lane >= (uint32_t)offset) { inclusive += other; }
-    }
-    warp_sums[warp][lane] = inclusive - value;
-  }
-  __syncthreads();
-#pragma unroll
-  for(int k = 0; k < 25; k++) { running[k] += warp_sums[k][warp]; }
-
-  for(int r = 0; r < PAIR_RECORDS_PER_THREAD; r++)
-  {
-    uint64_t record = first + r;
-    if(record >= n_pair_records) { break; }
-    uint32_t* words = pair_words + record * PAIR_WORDS;
-    // 25 x 20 bits -> words 16..31
-    uint64_t accumulator = 0; int bits = 0, word = 16;
-#pragma unroll
-    for(int k = 0; k < 25; k++)
-    {
-      accumulator |= (uint64_t)(running[k] & PAIR_FIELD_MASK) << bits; bits += 20;
-      if(bits >= 32) { words[word++] = (uint32_t)accumulator; accumulator >>= 32; bits -= 32; }
-    }
-    words[word++] = (uint32_t)accumulator;   // bits 480..499 end in word 31
-    // single counters: header of the basic record (+ its first half for the odd pair record)
-    {
-      const uint4* basic = idx.records + 4 * (record >> 1);
-      uint4 q0 = __ldg(basic), q1 = __ldg(basic + 1), q2 = __ldg(basic + 2), q3 = __ldg(basic + 3);
-      uint64_t field[SIGMA];
-#pragma unroll
-      for(uint32_t c = 1; c < SIGMA; c++)
-      {
-        field[c] = header_field(q0.w, q1.w, q2.w, q3.w, c);
-        if(record & 1) { field[c] += __popc(match_mask(q0, c)) + __popc(match_mask(q1, c)); }
-      }
-      uint64_t lo = field[1] | (field[2] << 25) | (field[3] << 50);
-      uint64_t hi = (field[3] >> 14) | (field[4] << 11) | (field[5] << 36);
-      words[6] = (uint32_t)lo; words[7] = (uint32_t)(lo >> 32); words[14] = (uint32_t)hi; words[15] = (uint32_t)(hi >> 32);
-    }
-    pair_record_counts(words, running);
   }
 }
 
@@ -270,11 +297,9 @@ int ensure_pair_index(bwtm_index* index, cudaStream_t stream)
   DeviceIndex view = device_view(index);
   pairs_gather<<<(unsigned)div_up(grid_chunks, 256), 256, 0, stream>>>(view, n_chunks, pairs.as<uint32_t>());
   BWTM_LAUNCH_CHECK();
-  pairs_count<<<(unsigned)n_pair_super, PAIR_FILL_THREADS, 0, stream>>>(pairs.as<uint32_t>(), n_pair_records, totals.as<unsigned long long>());
+  pairs_fill<<<(unsigned)n_pair_super, PAIR_FILL_THREADS, 0, stream>>>(view, pairs.as<uint32_t>(), n_pair_records, totals.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
   pairs_super<<<1, PAIR_SUPER_STRIDE, 0, stream>>>(view, totals.as<unsigned long long>(), n_pair_super, super2.as<uint64_t>());
-  BWTM_LAUNCH_CHECK();
-  pairs_fill<<<(unsigned)n_pair_super, PAIR_FILL_THREADS, 0, stream>>>(view, pairs.as<uint32_t>(), n_pair_records);
   BWTM_LAUNCH_CHECK();
   index->pair_bytes = pairs.bytes + super2.bytes;
   index->device_bytes += index->pair_bytes;
@@ -318,15 +343,8 @@ int prepare_walk(bwtm_index* a, bwtm_index* b, uint64_t walked_bases, cudaStream
     const uint64_t build = (a->d_pairs == nullptr ? a->size : 0) + (b->d_pairs == nullptr ? b->size : 0);
     want = (build <= 4 * walked_bases);
     // 2 bytes per symbol on top of the basic records: not when that would crowd out the rank array itself.
-    size_t free_bytes = 0, total_bytes = 0;
-    if(want && cudaMemGetInfo(&free_bytes, &total_bytes) == cudaSuccess)
-    {
-      uint64_t needed = (a->d_pairs == nullptr ? pair_index_bytes(a->size) : 0) + (b->d_pairs == nullptr ? pair_index_bytes(b->size) : 0);
-      uint64_t resident = pair_index_bytes(a->size) + pair_index_bytes(b->size);
-      if(resident > total_bytes / 3) { want = false; }
-      (void)needed;
-    }
-    cudaGetLastError();
+    const uint64_t total_bytes = device_total_bytes();
+    if(want && total_bytes > 0 && pair_index_bytes(a->size) + pair_index_bytes(b->size) > total_bytes / 3) { want = false; }
   }
   if(want)
   {

@@ -528,6 +528,297 @@ local_counting_sort(const KeyT* __restrict__ in, KeyT* __restrict__ out, const u
   }
 }
 
+//------------------------------------------------------------------------------
+// High key bits: most-significant-digit partition passes.
+//
+// The counting pass above finishes the low bits of every range on its own, so the high bits only have to be
+// PARTITIONED, not sorted stably: an MSD pass may place the keys of a bucket in any order. That removes what makes
+// a general radix pass expensive (the chained scan that gives every tile its place in every bucket): a CTA
+// histograms its tile, claims room in each bucket with one atomic add per non-empty bin, and writes its keys bucket
+// by bucket from shared memory. Two passes of up to 10 bits replace the library's onesweep passes
+// (latency-bound at 18 % of DRAM bandwidth on B200, profiles/r01_cub_sort_tuning_sweep*.txt).
+
+constexpr int MSD_THREADS  = 512;
+constexpr int MSD_ITEMS    = 16;
+constexpr int MSD_TILE     = MSD_THREADS * MSD_ITEMS;   // 8192 keys
+constexpr int MSD_MAX_BINS = 1024;
+
+// Segment s of a level holds the keys [bounds[s], bounds[s + 1]) and is cut into tiles; tile_first[s] is the index of
+// its first tile (tile_first[segments] = number of tiles). Returns false for a CTA beyond the last tile.
+__device__ __forceinline__ bool msd_locate_tile(const unsigned long long* __restrict__ bounds, const unsigned int* __restrict__ tile_first,
+                                                unsigned int segments, unsigned int tile, unsigned int& segment, uint64_t& begin, uint64_t& end)
+{
+  if(tile >= tile_first[segments]) { return false; }
+  unsigned int lo = 0, hi = segments;   // last segment with tile_first <= tile
+  while(hi - lo > 1)
+  {
+    unsigned int mid = (lo + hi) >> 1;
+    if(tile_first[mid] <= tile) { lo = mid; } else { hi = mid; }
+  }
+  segment = lo;
+  begin = bounds[lo] + (uint64_t)(tile - tile_first[lo]) * MSD_TILE;
+  end = bounds[lo + 1];
+  if(end > begin + MSD_TILE) { end = begin + MSD_TILE; }
+  return true;
+}
+
+// counts[segment * bins + digit] += number of keys of the tile with that digit.
+template<class KeyT>
+__global__ void __launch_bounds__(MSD_THREADS)
+msd_histogram(const KeyT* __restrict__ keys, const unsigned long long* __restrict__ bounds, const unsigned int* __restrict__ tile_first,
+              unsigned int segments, int shift, unsigned int bins, unsigned long long* __restrict__ counts)
+{
+  __shared__ unsigned int histogram[MSD_MAX_BINS];
+  __shared__ unsigned int s_segment; __shared__ unsigned long long s_begin, s_end; __shared__ int s_valid;
+  if(threadIdx.x == 0)
+  {
+    unsigned int segment = 0; uint64_t begin = 0, end = 0;
+    s_valid = msd_locate_tile(bounds, tile_first, segments, blockIdx.x, segment, begin, end) ? 1 : 0;
+    s_segment = segment; s_begin = begin; s_end = end;
+  }
+  for(unsigned int d = threadIdx.x; d < bins; d += MSD_THREADS) { histogram[d] = 0; }
+  __syncthreads();
+  if(!s_valid) { return; }
+  const uint64_t begin = s_begin, end = s_end;
+  const unsigned int mask = bins - 1;
+  for(uint64_t k = begin + threadIdx.x; k < end; k += MSD_THREADS) { atomicAdd(&histogram[(unsigned int)(keys[k] >> shift) & mask], 1u); }
+  __syncthreads();
+  for(unsigned int d = threadIdx.x; d < bins; d += MSD_THREADS)
+  {
+    if(histogram[d] != 0) { atomicAdd(&counts[(uint64_t)s_segment * bins + d], (unsigned long long)histogram[d]); }
+  }
+}
+
+// One CTA per segment: counts -> cursors (absolute output index of the next key of every bin) and the segment table
+// of the next level (sub-segment segment * bins + digit): bounds and tiles.
+__global__ void __launch_bounds__(MSD_MAX_BINS)
+msd_cursors(const unsigned long long* __restrict__ counts, const unsigned long long* __restrict__ bounds, unsigned int bins,
+            unsigned long long* __restrict__ cursors, unsigned long long* __restrict__ next_bounds, unsigned int* __restrict__ next_tiles)
+{
+  __shared__ unsigned long long warp_totals[MSD_MAX_BINS / 32];
+  const unsigned int d = threadIdx.x, lane = d & 31, warp = d >> 5;
+  const uint64_t slot = (uint64_t)blockIdx.x * bins + d;
+  unsigned long long mine = (d < bins ? counts[slot] : 0), inclusive = mine;
+#pragma unroll
+  for(int offset = 1; offset < 32; offset <<= 1)
+  {
+    unsigned long long other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+    if(lane >= (unsigned int)offset) { inclusive += other; }
+  }
+  if(lane == 31) { warp_totals[warp] = inclusive; }
+  __syncthreads();
+  if(warp == 0)
+  {
+    unsigned long long value = (lane < blockDim.x / 32 ? warp_totals[lane] : 0), scanned = value;
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+      unsigned long long other = __shfl_up_sync(0xFFFFFFFFu, scanned, offset);
+      if(lane >= (unsigned int)offset) { scanned += other; }
+    }
+    if(lane < blockDim.x / 32) { warp_totals[lane] = scanned - value; }
+  }
+  __syncthreads();
+  if(d >= bins) { return; }
+  unsigned long long start = bounds[blockIdx.x] + warp_totals[warp] + inclusive - mine;
+  cursors[slot] = start;
+  next_bounds[slot] = start;
+  next_tiles[slot] = (unsigned int)((mine + MSD_TILE - 1) / MSD_TILE);   // scanned by msd_tile_scan
+  if(blockIdx.x == gridDim.x - 1 && d == bins - 1) { next_bounds[slot + 1] = start + mine; }
+}
+
+// In-place exclusive scan of the tile counts of a level (entries + 1 values; the last one becomes the total).
+__global__ void __launch_bounds__(1024)
+msd_tile_scan(unsigned int* __restrict__ tiles, uint64_t entries)
+{
+  __shared__ unsigned int warp_totals[32];
+  __shared__ unsigned int carry;
+  if(threadIdx.x == 0) { carry = 0; }
+  __syncthreads();
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for(uint64_t base = 0; base < entries; base += 1024)
+  {
+    uint64_t k = base + threadIdx.x;
+    unsigned int mine = (k < entries ? tiles[k] : 0), inclusive = mine;
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+      unsigned int other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+      if(lane >= (unsigned int)offset) { inclusive += other; }
+    }
+    if(lane == 31) { warp_totals[warp] = inclusive; }
+    __syncthreads();
+    if(warp == 0)
+    {
+      unsigned int value = warp_totals[lane], scanned = value;
+#pragma unroll
+      for(int offset = 1; offset < 32; offset <<= 1)
+      {
+        unsigned int other = __shfl_up_sync(0xFFFFFFFFu, scanned, offset);
+        if(lane >= (unsigned int)offset) { scanned += other; }
+      }
+      warp_totals[lane] = scanned - value;
+    }
+    __syncthreads();
+    unsigned int exclusive = carry + warp_totals[warp] + inclusive - mine;
+    if(k < entries) { tiles[k] = exclusive; }
+    __syncthreads();
+    if(threadIdx.x == 1023) { carry = exclusive + mine; }
+    __syncthreads();
+  }
+  if(threadIdx.x == 0) { tiles[entries] = carry; }
+}
+
+// The partition pass: keys of a tile go to their buckets in `out`, in any order within a bucket.
+template<class KeyT>
+__global__ void __launch_bounds__(MSD_THREADS)
+msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned long long* __restrict__ bounds,
+            const unsigned int* __restrict__ tile_first, unsigned int segments, int shift, unsigned int bins,
+            unsigned long long* __restrict__ cursors)
+{
+  extern __shared__ __align__(16) unsigned char msd_shared[];
+  KeyT* staged = reinterpret_cast<KeyT*>(msd_shared);   // MSD_TILE keys
+  __shared__ unsigned int histogram[MSD_MAX_BINS];      // count, then the bin's first slot in `staged`
+  __shared__ unsigned long long target[MSD_MAX_BINS];   // output index of the bin's first key minus its first slot
+  __shared__ unsigned int warp_totals[MSD_THREADS / 32];
+  __shared__ unsigned int s_segment; __shared__ unsigned long long s_begin, s_end; __shared__ int s_valid;
+  if(threadIdx.x == 0)
+  {
+    unsigned int segment = 0; uint64_t begin = 0, end = 0;
+    s_valid = msd_locate_tile(bounds, tile_first, segments, blockIdx.x, segment, begin, end) ? 1 : 0;
+    s_segment = segment; s_begin = begin; s_end = end;
+  }
+  for(unsigned int d = threadIdx.x; d < bins; d += MSD_THREADS) { histogram[d] = 0; }
+  __syncthreads();
+  if(!s_valid) { return; }
+  const uint64_t begin = s_begin;
+  const unsigned int count = (unsigned int)(s_end - s_begin), mask = bins - 1;
+  const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+  KeyT keys[MSD_ITEMS]; unsigned int rank[MSD_ITEMS];
+#pragma unroll
+  for(int i = 0; i < MSD_ITEMS; i++)
+  {
+    unsigned int k = threadIdx.x + i * MSD_THREADS;
+    keys[i] = (k < count ? in[begin + k] : (KeyT)0);
+  }
+#pragma unroll
+  for(int i = 0; i < MSD_ITEMS; i++)
+  {
+    unsigned int k = threadIdx.x + i * MSD_THREADS;
+    rank[i] = (k < count ? atomicAdd(&histogram[(unsigned int)(keys[i] >> shift) & mask], 1u) : 0u);
+  }
+  __syncthreads();
+
+  // Room in the buckets (one atomic per non-empty bin) and the bins' places in the staging area: exclusive scan of
+  // the counts, two bins per thread (bins <= 2 * MSD_THREADS).
+  {
+    unsigned int d0 = 2 * threadIdx.x, d1 = d0 + 1;
+    unsigned int c0 = (d0 < bins ? histogram[d0] : 0), c1 = (d1 < bins ? histogram[d1] : 0);
+    unsigned int sum = c0 + c1, inclusive = sum;
+#pragma unroll
+    for(int offset = 1; offset < 32; offset <<= 1)
+    {
+      unsigned int other = __shfl_up_sync(0xFFFFFFFFu, inclusive, offset);
+      if(lane >= (unsigned int)offset) { inclusive += other; }
+    }
+    if(lane == 31) { warp_totals[warp] = inclusive; }
+    __syncthreads();
+    if(warp == 0)
+    {
+      unsigned int value = (lane < MSD_THREADS / 32 ? warp_totals[lane] : 0), scanned = value;
+#pragma unroll
+      for(int offset = 1; offset < 32; offset <<= 1)
+      {
+        unsigned int other = __shfl_up_sync(0xFFFFFFFFu, scanned, offset);
+        if(lane >= (unsigned int)offset) { scanned += other; }
+      }
+      if(lane < MSD_THREADS / 32) { warp_totals[lane] = scanned - value; }
+    }
+    __syncthreads();
+    unsigned int first0 = warp_totals[warp] + inclusive - sum, first1 = first0 + c0;
+    unsigned long long* row = cursors + (uint64_t)s_segment * bins;
+    if(d0 < bins) { histogram[d0] = first0; if(c0 != 0) { target[d0] = atomicAdd(row + d0, (unsigned long long)c0) - first0; } }
+    if(d1 < bins) { histogram[d1] = first1; if(c1 != 0) { target[d1] = atomicAdd(row + d1, (unsigned long long)c1) - first1; } }
+  }
+  __syncthreads();
+#pragma unroll
+  for(int i = 0; i < MSD_ITEMS; i++)
+  {
+    unsigned int k = threadIdx.x + i * MSD_THREADS;
+    if(k < count) { staged[histogram[(unsigned int)(keys[i] >> shift) & mask] + rank[i]] = keys[i]; }
+  }
+  __syncthreads();
+  for(unsigned int k = threadIdx.x; k < count; k += MSD_THREADS)
+  {
+    KeyT key = staged[k];
+    out[target[(unsigned int)(key >> shift) & mask] + k] = key;
+  }
+}
+
+// Partitions keys[0, n) by the bits [low_bit, high_bit) with one or two MSD passes (at most 20 bits). On return
+// *where holds the partitioned keys (d_keys or d_alt) and d_offsets[r] (r = 0 .. 2^(high_bit - low_bit)) is the index
+// of the first key whose bits are >= r: the ranges of the counting pass.
+template<class KeyT>
+static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int high_bit, unsigned long long* d_offsets,
+                         KeyT** where, cudaStream_t stream)
+{
+  const int total_bits = high_bit - low_bit;
+  const int levels = (total_bits > 10 ? 2 : 1);
+  const int bits1 = (levels == 1 ? total_bits : (total_bits + 1) / 2), bits2 = total_bits - bits1;
+  const unsigned int bins1 = 1u << bits1, bins2 = 1u << bits2;
+  const uint64_t ranges = 1ull << total_bits;
+
+  // level tables: bounds (entries + 1), tile_first (entries + 1), counts / cursors (entries x bins)
+  DeviceBuffer bounds1, tiles1, counts1, cursors1, bounds2, tiles2, counts2;
+  BWTM_TRY(bounds1.allocate(2 * sizeof(unsigned long long))); BWTM_TRY(tiles1.allocate(2 * sizeof(unsigned int)));
+  BWTM_TRY(counts1.allocate(bins1 * sizeof(unsigned long long))); BWTM_TRY(cursors1.allocate(bins1 * sizeof(unsigned long long)));
+  BWTM_TRY(bounds2.allocate((bins1 + 1) * sizeof(unsigned long long))); BWTM_TRY(tiles2.allocate((bins1 + 1) * sizeof(unsigned int)));
+  const unsigned long long host_bounds[2] = { 0, n };
+  const unsigned int tiles_level1 = (unsigned int)div_up(n, MSD_TILE);
+  const unsigned int host_tiles[2] = { 0, tiles_level1 };
+  BWTM_CUDA(cudaMemcpyAsync(bounds1.ptr, host_bounds, sizeof(host_bounds), cudaMemcpyHostToDevice, stream));
+  BWTM_CUDA(cudaMemcpyAsync(tiles1.ptr, host_tiles, sizeof(host_tiles), cudaMemcpyHostToDevice, stream));
+  BWTM_CUDA(cudaMemsetAsync(counts1.ptr, 0, bins1 * sizeof(unsigned long long), stream));
+
+  // level 1 (the most significant bits)
+  const int shift1 = low_bit + bits2;
+  msd_histogram<KeyT><<<tiles_level1, MSD_THREADS, 0, stream>>>(d_keys, bounds1.as<unsigned long long>(), tiles1.as<unsigned int>(), 1, shift1, bins1,
+                                                                 counts1.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  unsigned long long* level1_bounds = (levels == 1 ? d_offsets : bounds2.as<unsigned long long>());
+  msd_cursors<<<1, std::max(32u, bins1), 0, stream>>>(counts1.as<unsigned long long>(), bounds1.as<unsigned long long>(), bins1,
+                                                      cursors1.as<unsigned long long>(), level1_bounds, tiles2.as<unsigned int>());
+  BWTM_LAUNCH_CHECK();
+  const size_t staged_bytes = (size_t)MSD_TILE * sizeof(KeyT);
+  BWTM_CUDA(cudaFuncSetAttribute(msd_scatter<KeyT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)staged_bytes));
+  msd_scatter<KeyT><<<tiles_level1, MSD_THREADS, staged_bytes, stream>>>(d_keys, d_alt, bounds1.as<unsigned long long>(), tiles1.as<unsigned int>(), 1, shift1, bins1,
+                                                               cursors1.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  if(levels == 1) { *where = d_alt; return BWTM_OK; }
+
+  // level 2: every bucket of level 1 is a segment
+  msd_tile_scan<<<1, 1024, 0, stream>>>(tiles2.as<unsigned int>(), bins1);
+  BWTM_LAUNCH_CHECK();
+  BWTM_TRY(counts2.allocate(ranges * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemsetAsync(counts2.ptr, 0, ranges * sizeof(unsigned long long), stream));
+  const unsigned int tiles_level2 = tiles_level1 + bins1;   // upper bound: every segment wastes less than one tile
+  msd_histogram<KeyT><<<tiles_level2, MSD_THREADS, 0, stream>>>(d_alt, bounds2.as<unsigned long long>(), tiles2.as<unsigned int>(), bins1, low_bit, bins2,
+                                                                 counts2.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  // The cursors of level 2 are written over the counts; their initial values are the range offsets.
+  DeviceBuffer cursors2, unused_tiles;
+  BWTM_TRY(cursors2.allocate(ranges * sizeof(unsigned long long))); BWTM_TRY(unused_tiles.allocate((ranges + 1) * sizeof(unsigned int)));
+  msd_cursors<<<bins1, std::max(32u, bins2), 0, stream>>>(counts2.as<unsigned long long>(), bounds2.as<unsigned long long>(), bins2,
+                                                          cursors2.as<unsigned long long>(), d_offsets, unused_tiles.as<unsigned int>());
+  BWTM_LAUNCH_CHECK();
+  msd_scatter<KeyT><<<tiles_level2, MSD_THREADS, staged_bytes, stream>>>(d_alt, d_keys, bounds2.as<unsigned long long>(), tiles2.as<unsigned int>(), bins1, low_bit, bins2,
+                                                               cursors2.as<unsigned long long>());
+  BWTM_LAUNCH_CHECK();
+  *where = d_keys;
+  return BWTM_OK;
+}
+
 static uint64_t env_number(const char* name, uint64_t fallback)
 {
   const char* text = getenv(name);
@@ -558,13 +849,24 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
     return BWTM_OK;
   }
 
-  BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, local_bits, bits, stream));
   const uint64_t ranges = std::min<uint64_t>(1ull << (bits - local_bits), ((key_limit - 1) >> local_bits) + 1);
-  DeviceBuffer offsets; BWTM_TRY(offsets.allocate((ranges + 1) * sizeof(unsigned long long)));
+  DeviceBuffer offsets; BWTM_TRY(offsets.allocate(((1ull << (bits - local_bits)) + 1) * sizeof(unsigned long long)));
   DeviceBuffer heavy; BWTM_TRY(heavy.allocate((2 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long)));
   BWTM_CUDA(cudaMemsetAsync(heavy.ptr, 0, (2 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long), stream));
-  range_offsets<KeyT><<<(unsigned)div_up(ranges + 1, 256), 256, 0, stream>>>(buffers.Current(), n, local_bits, ranges, offsets.as<unsigned long long>());
-  BWTM_LAUNCH_CHECK();
+  // The high bits: MSD partition passes (they also deliver the range offsets), or the library's radix passes
+  // (BWTM_MSD=0, and keys with more than 20 high bits).
+  if(bits - local_bits <= 20 && env_number("BWTM_MSD", 1) != 0)
+  {
+    KeyT* where = nullptr;
+    BWTM_TRY(msd_partition<KeyT>(d_keys, d_alt, n, local_bits, bits, offsets.as<unsigned long long>(), &where, stream));
+    if(where != buffers.Current()) { buffers.selector ^= 1; }
+  }
+  else
+  {
+    BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, local_bits, bits, stream));
+    range_offsets<KeyT><<<(unsigned)div_up(ranges + 1, 256), 256, 0, stream>>>(buffers.Current(), n, local_bits, ranges, offsets.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+  }
   range_heavy<<<(unsigned)div_up(ranges, 256), 256, 0, stream>>>(offsets.as<unsigned long long>(), ranges, small_keys, local_limit, heavy.as<unsigned long long>());
   BWTM_LAUNCH_CHECK();
   const uint32_t half_words = 1u << (local_bits - 1);
