@@ -88,13 +88,34 @@ k4_interleave(DeviceIndex a, DeviceIndex b, const KeyT* __restrict__ keys, uint6
   if(tid < TILE / 32) { bitmap[tid] = 0; }
   __syncthreads();
   uint32_t new_values = 0;   // RA values that differ from their predecessor: the reference's RA run count
-  for(uint64_t k = tid; k < j1 - j0; k += IL_THREADS)
   {
-    uint64_t j = j0 + k;
-    KeyT key = keys[j - key_base];
-    uint32_t q = (uint32_t)(j + (uint64_t)key - d0);
-    atomicOr(&bitmap[q >> 5], 1u << (q & 31u));
-    new_values += (j == key_base || keys[j - key_base - 1] != key) ? 1u : 0u;
+    // Every thread takes a contiguous share of the tile's keys: their merged positions j + RA[j] increase, so the
+    // bits of a share fall into a few consecutive words that are collected in a register and written once each
+    // (one atomic per key made the sorted keys of a warp collide on the same word: 292 M bank conflicts per 2^30
+    // positions, profiles/r02_k4k5_ncu.txt).
+    const uint32_t total = (uint32_t)(j1 - j0), share = (total + IL_THREADS - 1) / IL_THREADS;
+    const uint32_t first = min(tid * share, total), last = min(first + share, total);
+    if(first < last)
+    {
+      const KeyT* mine = keys + (j0 - key_base);
+      KeyT previous = (j0 + first > key_base ? mine[(int64_t)first - 1] : (KeyT)0);
+      bool no_previous = (j0 + first == key_base);
+      uint32_t word = 0xFFFFFFFFu, collected = 0;
+      for(uint32_t k = first; k < last; k++)
+      {
+        KeyT key = mine[k];
+        uint32_t q = (uint32_t)(j0 + k + (uint64_t)key - d0);
+        if((q >> 5) != word)
+        {
+          if(collected != 0) { atomicOr(&bitmap[word], collected); }
+          word = q >> 5; collected = 0;
+        }
+        collected |= 1u << (q & 31u);
+        new_values += (no_previous || key != previous) ? 1u : 0u;
+        previous = key; no_previous = false;
+      }
+      if(collected != 0) { atomicOr(&bitmap[word], collected); }
+    }
   }
   if(distinct_keys != nullptr && new_values != 0) { atomicAdd(&distinct, new_values); }
   __syncthreads();

@@ -55,6 +55,21 @@ def test_config1_in_five_search_batches_equals_reference_binary():
     assert got == {k: known[k] for k in got}
 
 
+@pytest.mark.parametrize("wide", [False, True])
+def test_config1_through_two_msd_partition_levels(monkeypatch, wide):
+    """Config 1 has 24-bit keys: with the counting pass forced on (12 low bits) the 12 high bits take two MSD partition
+    levels of 6 bits; with 64-bit keys as well. The result must still be the reference binary's."""
+    monkeypatch.setenv("BWTM_LOCAL_SORT_MIN", "1"); monkeypatch.setenv("BWTM_LOCAL_SORT_DENSITY", "0")
+    monkeypatch.setenv("BWTM_LOCAL_SORT_MAX_DENSITY", "0")
+    if wide:
+        monkeypatch.setenv("BWTM_FORCE_WIDE", "1")
+    got, known = merged_digest(1)
+    assert got == {k: known[k] for k in got}
+    monkeypatch.setenv("BWTM_MSD", "0")        # the library's radix passes for the high bits: same bytes
+    got, known = merged_digest(1)
+    assert got == {k: known[k] for k in got}
+
+
 def test_config2_full_size_equals_reference_binary():
     got, known = merged_digest(2)
     assert got == {k: known[k] for k in got}
