@@ -251,14 +251,6 @@ static void writeSparse(std::ostream& out, size_type universe, const std::vector
   out.write(reinterpret_cast<const char*>(high.data()), 8 * layout.high_words);
 }
 
-static bool skipSparse(std::istream& in)
-{
-  size_type size = 0, ones = 0; byte_type width = 0;
-  if(!readPod(in, size) || !readPod(in, ones) || !readPod(in, width)) { return false; }
-  SparseLayout layout(size, ones);
-  in.seekg(8 * (layout.low_words + layout.high_words), std::ios::cur);
-  return (bool)in;
-}
 
 //------------------------------------------------------------------------------
 // HostBWT
@@ -442,25 +434,48 @@ static void finishLoaded(HostBWT& bwt, AlphabeticOrder order)   // BWT::setHeade
   bwt.alpha.setCounts(bwt.counts);
 }
 
+// Native files (bwt.cpp:111-148, fmi.cpp: serialize): NativeHeader, BlockArray, seven sparse vectors with their
+// support structures, Alphabet. Only the header, the run-length bytes and the alphabet are needed here (the rank
+// structure is rebuilt on the device), and the sparse vectors are the one part whose byte layout belongs to SDSL
+// (unpinned). So they are not parsed at all: the Alphabet is the LAST section and has a fixed
+// size (int_vector<8>[256], int_vector<8>[6], int_vector<64>[7], u64 sigma = 352 bytes, support.cpp:160-171) and is
+// read from the end of the file. A file written by a reference built with the real SDSL loads the same way.
 static bool loadNative(HostBWT& bwt, std::ifstream& in)
 {
   std::uint32_t tag = 0, flags = 0;
   readPod(in, tag); readPod(in, flags); readPod(in, bwt.sequences); readPod(in, bwt.bases);
   if(!in || tag != 0x54574221u) { std::cerr << "BWT::load(): Invalid header!" << std::endl; return false; }
   size_type bytes = 0; readPod(in, bytes);
+  const size_type stored = ((bytes + ARRAY_BLOCK - 1) / ARRAY_BLOCK) * ARRAY_BLOCK;
+  const size_type ALPHABET_BYTES = (8 + 256) + (8 + 8) + (8 + 8 * (SIGMA + 1)) + 8;
+  const std::streampos payload = in.tellg();
+  in.seekg(0, std::ios::end);
+  const size_type file_size = (size_type)in.tellg();
+  if(!in || (size_type)payload + stored + ALPHABET_BYTES > file_size)
+  {
+    std::cerr << "BWT::load(): Truncated native file (" << bytes << " bytes of run-length code announced)" << std::endl;
+    return false;
+  }
+  in.seekg(payload);
   bwt.rle.resize(bytes);
   in.read(reinterpret_cast<char*>(bwt.rle.data()), bytes);
-  size_type stored = ((bytes + ARRAY_BLOCK - 1) / ARRAY_BLOCK) * ARRAY_BLOCK;
-  in.seekg(stored - bytes, std::ios::cur);
-  for(size_type c = 0; c < SIGMA; c++) { size_type m_size = 0; if(!skipSparse(in) || !readPod(in, m_size)) { return false; } }
-  if(!skipSparse(in)) { return false; }
-  // Alphabet: int_vector<8>[256], int_vector<8>[6], int_vector<64>[7], u64 sigma (support.cpp:160-180)
-  size_type bits = 0;
-  readPod(in, bits); in.read(reinterpret_cast<char*>(bwt.alpha.char2comp), 256);
-  readPod(in, bits); in.read(reinterpret_cast<char*>(bwt.alpha.comp2char), SIGMA); in.seekg(8 - SIGMA, std::ios::cur);
-  readPod(in, bits); in.read(reinterpret_cast<char*>(bwt.alpha.C), 8 * (SIGMA + 1));
+
+  in.seekg(file_size - ALPHABET_BYTES);
+  size_type bits_char2comp = 0, bits_comp2char = 0, bits_C = 0;
+  byte_type padded[8];
+  readPod(in, bits_char2comp); in.read(reinterpret_cast<char*>(bwt.alpha.char2comp), 256);
+  readPod(in, bits_comp2char); in.read(reinterpret_cast<char*>(padded), 8);
+  readPod(in, bits_C); in.read(reinterpret_cast<char*>(bwt.alpha.C), 8 * (SIGMA + 1));
   readPod(in, bwt.alpha.sigma);
-  if(!in) { std::cerr << "BWT::load(): Invalid header!" << std::endl; return false; }
+  for(size_type c = 0; c < SIGMA; c++) { bwt.alpha.comp2char[c] = padded[c]; }
+  bool plausible = (bool)in && bits_char2comp == 8 * 256 && bits_comp2char == 8 * SIGMA && bits_C == 64 * (SIGMA + 1) && bwt.alpha.sigma == SIGMA &&
+                   bwt.alpha.C[0] == 0 && bwt.alpha.C[SIGMA] == bwt.bases;
+  for(size_type c = 0; plausible && c < SIGMA; c++) { plausible = (bwt.alpha.C[c] <= bwt.alpha.C[c + 1]); }
+  if(!plausible)
+  {
+    std::cerr << "BWT::load(): Cannot find the alphabet at the end of the native file: not written by bwt_merge / bwt_convert, or with another alphabet size" << std::endl;
+    return false;
+  }
   for(size_type c = 0; c < SIGMA; c++) { bwt.counts[c] = bwt.alpha.C[c + 1] - bwt.alpha.C[c]; }
   return true;
 }

@@ -63,3 +63,24 @@ def test_plain_reader_quirks(oracle, tools, tmp_path):
     a, b = str(tmp_path / "a.native"), str(tmp_path / "b.native")
     run(mine, src, a, "plain_default", "native"); run(ref, src, b, "plain_default", "native")
     assert filecmp.cmp(a, b, shallow=False)
+
+
+def test_native_loader_does_not_depend_on_the_sparse_vector_layout(oracle, tools, tmp_path):
+    """The seven sparse vectors of a native file are SDSL's to lay out; the loader reads the header,
+    the run-length bytes and the alphabet (the last 352 bytes) and skips whatever lies between. A file whose sample
+    section has another size (as a real-SDSL build would write it) must load; malformed files must fail with a message."""
+    mine, ref = tools
+    reads, bwt = make_collection(oracle, 1500, 300, 50, 0.02, 42, 7)
+    src = str(tmp_path / "src.plain"); synth.comps_to_chars(bwt).tofile(src)
+    native = str(tmp_path / "a.native"); run(ref, src, native, "plain_default", "native")
+    data = open(native, "rb").read()
+    rle_bytes = int(np.frombuffer(data[24:32], dtype=np.uint64)[0])
+    payload_end = 32 + ((rle_bytes + (8 << 20) - 1) // (8 << 20)) * (8 << 20)
+    foreign = str(tmp_path / "foreign.native")
+    open(foreign, "wb").write(data[:payload_end] + bytes(np.random.default_rng(1).integers(0, 256, 12345, dtype=np.uint8)) + data[-352:])
+    back = str(tmp_path / "back.plain"); run(mine, foreign, back, "native", "plain_default")
+    assert filecmp.cmp(back, src, shallow=False)
+    for name, blob in (("truncated", data[:payload_end - 100]), ("no_alphabet", data[:payload_end] + b"\0" * 400)):
+        bad = str(tmp_path / (name + ".native")); open(bad, "wb").write(blob)
+        res = subprocess.run([mine, "-i", "native", "-o", "plain_default", bad, str(tmp_path / "out")], capture_output=True, text=True)
+        assert res.returncode != 0 and "BWT::load()" in res.stderr, name
