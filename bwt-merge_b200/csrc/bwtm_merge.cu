@@ -1540,9 +1540,18 @@ static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* op
   EventTimer timer(stream);
   KeyT* sorted = nullptr;
   {
+    // The first partition level of the sort needs the histogram of its digit: the walk counts it while it writes.
+    WalkHistogram histogram = { nullptr, 0, 1 };
+    DeviceBuffer digit_counts;
+    if(sort_plan_level1(n_b, bit_length_host(a->size), a->size + 1, &histogram.shift, &histogram.bins))
+    {
+      BWTM_TRY(digit_counts.allocate(histogram.bins * sizeof(unsigned long long)));
+      BWTM_CUDA(cudaMemsetAsync(digit_counts.ptr, 0, histogram.bins * sizeof(unsigned long long), stream));
+      histogram.counts = digit_counts.as<unsigned long long>();
+    }
     timer.start();
     uint64_t emitted = 0;
-    BWTM_TRY(walk_sequences<KeyT>(a, b, 0, b->sequences - 1, keys.as<KeyT>(), n_b, &emitted, stream));
+    BWTM_TRY(walk_sequences<KeyT>(a, b, 0, b->sequences - 1, keys.as<KeyT>(), n_b, &emitted, stream, &histogram));
     timings->search_seconds = timer.stop() * 1e-3;
     timings->walk_kernel_launches = 1;
     if(emitted != n_b)
@@ -1553,7 +1562,7 @@ static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* op
     }
     timings->ra_values = emitted;
     timer.start();
-    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream, a->size + 1));
+    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream, a->size + 1, histogram.counts));
     timings->sort_seconds = timer.stop() * 1e-3;
   }
   if(sorted == keys.as<KeyT>()) { alt.release(); } else { keys.release(); }

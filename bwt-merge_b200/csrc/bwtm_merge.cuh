@@ -6,21 +6,31 @@
 namespace bwtm
 {
 
+// Optional by-product of the walk: counts[(value >> shift) & (bins - 1)] += 1 for every emitted value, the histogram
+// of the first partition level of the sort (collected in shared memory while the values are flushed).
+struct WalkHistogram
+{
+  unsigned long long* counts;   // bins zeroed counters on the device, or null
+  int                 shift;
+  unsigned int        bins;     // power of two, at most 1024
+};
+
 // K1. Appends one RA value per suffix of the sequences [seq_first, seq_last] of b to d_out (unordered).
 template<class KeyT>
 int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
-                   KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream);
+                   KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream, const WalkHistogram* histogram = nullptr);
 
 // K1 without waiting: enqueues the walk on `stream`; RA values are appended at *cursor, which consecutive
 // launches may share. `counters` (walk_counters_bytes() zeroed bytes) is private to the launch.
 template<class KeyT>
 int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                          KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor,
-                         int max_blocks_per_sm, cudaStream_t stream);
+                         int max_blocks_per_sm, cudaStream_t stream, const WalkHistogram* histogram = nullptr);
 // K1, two-step form (bwtm_pairs.cu): both indexes carry pair records.
 template<class KeyT>
 int walk_pairs_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
-                     KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, cudaStream_t stream);
+                     KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, cudaStream_t stream,
+                     const WalkHistogram* histogram = nullptr);
 // Decides how b is walked against a and builds what that needs: pair records on both (two backward steps per
 // record read) when it pays for the `walked_bases` symbols of b this GPU searches and fits, else nothing (single-step walk on the basic records). Fills the walk_* fields
 // and pair_index_seconds of `timings`.
@@ -31,7 +41,11 @@ int walk_counters_check(const void* host_copy);   // non-zero: the output buffer
 
 // K2. Radix sort on the low `bits` bits; *sorted points into d_keys or d_alt.
 template<class KeyT>
-int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit = 0);   // key_limit: exclusive bound of the key values, when known
+int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit = 0,   // key_limit: exclusive bound of the key values, when known
+              const unsigned long long* level1_counts = nullptr);   // histogram delivered by the walk (sort_plan_level1)
+// True when sort_keys(n, bits, key_limit) partitions the high bits itself; then (shift, bins) describe the digit of its
+// first level, whose histogram the walk can deliver.
+bool sort_plan_level1(uint64_t n, int bits, uint64_t key_limit, int* shift, unsigned int* bins);
 
 // Sequential state of the byte encoder that crosses slabs (and GPU slices).
 struct EncodeControl

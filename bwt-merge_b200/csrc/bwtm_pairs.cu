@@ -455,15 +455,19 @@ __device__ __forceinline__ void complement_masks(uint32_t c, uint32_t& n0, uint3
 template<class KeyT, class PosT>
 __global__ void __launch_bounds__(PW_THREADS, 4)
 k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
-              KeyT* __restrict__ out, uint64_t capacity, PairWalkCounters* counters, unsigned long long* cursor)
+              KeyT* __restrict__ out, uint64_t capacity, PairWalkCounters* counters, unsigned long long* cursor, WalkHistogram histogram)
 {
   __shared__ KeyT stage_all[PW_WARPS][PW_STAGE];
+  __shared__ unsigned int digit_counts[1024];
   __shared__ __align__(16) uint32_t scratch_all[PW_WARPS][32 / PW_LANES][2][16];   // pair counters of A and B per walker
   __shared__ PosT c_a[8];
 
 #pragma unroll
   for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = (PosT)a.C[c]; } }
+  for(unsigned int d = threadIdx.x; d < 1024; d += PW_THREADS) { digit_counts[d] = 0; }
   __syncthreads();
+  const bool counting = (histogram.counts != nullptr);
+  const unsigned int digit_mask = histogram.bins - 1;
 
   const unsigned FULL = 0xFFFFFFFFu;
   const unsigned LEADERS = 0x11111111u;
@@ -524,7 +528,12 @@ k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
       base = __shfl_sync(FULL, base, 0);
       if(base + fill <= capacity)
       {
-        for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+        for(uint32_t k = lane; k < fill; k += 32)
+        {
+          KeyT value = stage[k];
+          out[base + k] = value;
+          if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+        }
       }
       else
       {
@@ -623,15 +632,29 @@ k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
     base = __shfl_sync(FULL, base, 0);
     if(base + fill <= capacity)
     {
-      for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+      for(uint32_t k = lane; k < fill; k += 32)
+        {
+          KeyT value = stage[k];
+          out[base + k] = value;
+          if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+        }
     }
     else if(lane == 0) { counters->overflow = 1; }
+  }
+  if(counting)
+  {
+    __syncthreads();
+    for(unsigned int d = threadIdx.x; d < histogram.bins; d += PW_THREADS)
+    {
+      if(digit_counts[d] != 0) { atomicAdd(histogram.counts + d, (unsigned long long)digit_counts[d]); }
+    }
   }
 }
 
 template<class KeyT, class PosT>
 static int launch_pairs(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
-                        KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, int sms, cudaStream_t stream)
+                        KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, int sms, cudaStream_t stream,
+                        WalkHistogram histogram)
 {
   int per_sm = 0;
   BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_pairs<KeyT, PosT>, PW_THREADS, 0));
@@ -639,7 +662,7 @@ static int launch_pairs(const bwtm_index* a, const bwtm_index* b, uint64_t seq_f
   uint64_t sequences = seq_last + 1 - seq_first;
   uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, PW_THREADS / PW_LANES));
   k1_walk_pairs<KeyT, PosT><<<(unsigned)blocks, PW_THREADS, 0, stream>>>(
-    pair_view(a), pair_view(b), seq_first, seq_last + 1, d_out, capacity, static_cast<PairWalkCounters*>(counters), cursor);
+    pair_view(a), pair_view(b), seq_first, seq_last + 1, d_out, capacity, static_cast<PairWalkCounters*>(counters), cursor, histogram);
   return BWTM_OK;
 }
 
@@ -647,8 +670,11 @@ static int launch_pairs(const bwtm_index* a, const bwtm_index* b, uint64_t seq_f
 // `counters` is walk_counters_bytes() zeroed bytes (same layout as the single-step walk's counters).
 template<class KeyT>
 int walk_pairs_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
-                     KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, cudaStream_t stream)
+                     KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, cudaStream_t stream,
+                     const WalkHistogram* histogram)
 {
+  WalkHistogram counting = { nullptr, 0, 1 };
+  if(histogram != nullptr && histogram->counts != nullptr && histogram->bins <= 1024) { counting = *histogram; }
   static_assert(sizeof(PairWalkCounters) == 24, "counter layout shared with the single-step walk");
   if(a->d_pairs == nullptr || b->d_pairs == nullptr) { set_error("pair records missing"); return BWTM_ERR_INTERNAL; }
   int device = 0, sms = 0;
@@ -656,18 +682,18 @@ int walk_pairs_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_firs
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr)
   {
-    BWTM_TRY((launch_pairs<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream)));
+    BWTM_TRY((launch_pairs<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream, counting)));
   }
   else
   {
-    BWTM_TRY((launch_pairs<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream)));
+    BWTM_TRY((launch_pairs<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream, counting)));
   }
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }
 
-template int walk_pairs_async<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, void*, unsigned long long*, cudaStream_t);
-template int walk_pairs_async<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, void*, unsigned long long*, cudaStream_t);
+template int walk_pairs_async<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, void*, unsigned long long*, cudaStream_t, const WalkHistogram*);
+template int walk_pairs_async<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, void*, unsigned long long*, cudaStream_t, const WalkHistogram*);
 
 } // namespace bwtm
 

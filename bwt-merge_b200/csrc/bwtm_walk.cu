@@ -75,14 +75,18 @@ __device__ __forceinline__ uint32_t coop_record_rank(const uint4& q, uint32_t of
 template<class KeyT, class PosT>
 __global__ void __launch_bounds__(WALK_THREADS, 8)
 k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
-             KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor)
+             KeyT* __restrict__ out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor, WalkHistogram histogram)
 {
   __shared__ KeyT stage_all[WALK_WARPS][WALK_STAGE];
   __shared__ PosT c_a[8], c_b[8];
+  __shared__ unsigned int digit_counts[1024];
 
 #pragma unroll
   for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = (PosT)a.C[c]; c_b[c] = (PosT)b.C[c]; } }
+  for(unsigned int d = threadIdx.x; d < 1024; d += WALK_THREADS) { digit_counts[d] = 0; }
   __syncthreads();
+  const bool counting = (histogram.counts != nullptr);
+  const unsigned int digit_mask = histogram.bins - 1;
 
   const unsigned FULL = 0xFFFFFFFFu;
   const unsigned LEADERS = 0x11111111u;
@@ -140,7 +144,12 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
       base = __shfl_sync(FULL, base, 0);
       if(base + fill <= capacity)
       {
-        for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+        for(uint32_t k = lane; k < fill; k += 32)
+        {
+          KeyT value = stage[k];
+          out[base + k] = value;
+          if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+        }
       }
       else
       {
@@ -178,16 +187,29 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
     base = __shfl_sync(FULL, base, 0);
     if(base + fill <= capacity)
     {
-      for(uint32_t k = lane; k < fill; k += 32) { out[base + k] = stage[k]; }
+      for(uint32_t k = lane; k < fill; k += 32)
+        {
+          KeyT value = stage[k];
+          out[base + k] = value;
+          if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+        }
     }
     else if(lane == 0) { counters->overflow = 1; }
+  }
+  if(counting)
+  {
+    __syncthreads();
+    for(unsigned int d = threadIdx.x; d < histogram.bins; d += WALK_THREADS)
+    {
+      if(digit_counts[d] != 0) { atomicAdd(histogram.counts + d, (unsigned long long)digit_counts[d]); }
+    }
   }
 }
 
 template<class KeyT, class PosT>
 static int launch_coop(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                        KeyT* d_out, uint64_t capacity, WalkCounters* counters, unsigned long long* cursor,
-                       int sms, int max_blocks_per_sm, cudaStream_t stream)
+                       int sms, int max_blocks_per_sm, cudaStream_t stream, WalkHistogram histogram)
 {
   int per_sm = 0;
   BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_coop<KeyT, PosT>, WALK_THREADS, 0));
@@ -196,7 +218,7 @@ static int launch_coop(const bwtm_index* a, const bwtm_index* b, uint64_t seq_fi
   uint64_t sequences = seq_last + 1 - seq_first;
   uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, WALK_THREADS / COOP_LANES));
   k1_walk_coop<KeyT, PosT><<<(unsigned)blocks, WALK_THREADS, 0, stream>>>(
-    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters, cursor);
+    device_view(a), device_view(b), seq_first, seq_last + 1, d_out, capacity, counters, cursor, histogram);
   return BWTM_OK;
 }
 
@@ -205,29 +227,31 @@ static int launch_coop(const bwtm_index* a, const bwtm_index* b, uint64_t seq_fi
 template<class KeyT>
 int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                          KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor,
-                         int max_blocks_per_sm, cudaStream_t stream)
+                         int max_blocks_per_sm, cudaStream_t stream, const WalkHistogram* histogram)
 {
+  WalkHistogram counting = { nullptr, 0, 1 };
+  if(histogram != nullptr && histogram->counts != nullptr && histogram->bins <= 1024) { counting = *histogram; }
   int device = 0, sms = 0;
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
   if(walk_uses_pairs(a, b))   // two backward steps per record read (bwtm_pairs.cu)
   {
-    return walk_pairs_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, stream);
+    return walk_pairs_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, stream, &counting);
   }
   if(a->size < 0xFFFFFFFFull && b->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr)
   {
-    BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream)));
+    BWTM_TRY((launch_coop<KeyT, uint32_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream, counting)));
   }
   else
   {
-    BWTM_TRY((launch_coop<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream)));
+    BWTM_TRY((launch_coop<KeyT, uint64_t>(a, b, seq_first, seq_last, d_out, capacity, static_cast<WalkCounters*>(counters), cursor, sms, max_blocks_per_sm, stream, counting)));
   }
   BWTM_LAUNCH_CHECK();
   return BWTM_OK;
 }
 
-template int walk_sequences_async<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, void*, unsigned long long*, int, cudaStream_t);
-template int walk_sequences_async<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, void*, unsigned long long*, int, cudaStream_t);
+template int walk_sequences_async<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, void*, unsigned long long*, int, cudaStream_t, const WalkHistogram*);
+template int walk_sequences_async<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, void*, unsigned long long*, int, cudaStream_t, const WalkHistogram*);
 
 uint64_t walk_counters_bytes() { return sizeof(WalkCounters); }
 
@@ -239,13 +263,13 @@ int walk_counters_check(const void* host_copy)
 
 template<class KeyT>
 int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
-                   KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream)
+                   KeyT* d_out, uint64_t capacity, uint64_t* emitted, cudaStream_t stream, const WalkHistogram* histogram)
 {
   DeviceBuffer counters; BWTM_TRY(counters.allocate(sizeof(WalkCounters)));
   BWTM_CUDA(cudaMemsetAsync(counters.ptr, 0, sizeof(WalkCounters), stream));
 
   unsigned long long* cursor = &(counters.as<WalkCounters>()->emitted);
-  BWTM_TRY(walk_sequences_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters.ptr, cursor, 0, stream));
+  BWTM_TRY(walk_sequences_async<KeyT>(a, b, seq_first, seq_last, d_out, capacity, counters.ptr, cursor, 0, stream, histogram));
 
   WalkCounters host;
   BWTM_CUDA(cudaMemcpyAsync(&host, counters.ptr, sizeof(WalkCounters), cudaMemcpyDeviceToHost, stream));
@@ -256,8 +280,8 @@ int walk_sequences(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first,
   return BWTM_OK;
 }
 
-template int walk_sequences<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, uint64_t*, cudaStream_t);
-template int walk_sequences<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, uint64_t*, cudaStream_t);
+template int walk_sequences<uint32_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint32_t*, uint64_t, uint64_t*, cudaStream_t, const WalkHistogram*);
+template int walk_sequences<uint64_t>(const bwtm_index*, const bwtm_index*, uint64_t, uint64_t, uint64_t*, uint64_t, uint64_t*, cudaStream_t, const WalkHistogram*);
 
 // K2: sort of the RA values (support.h:421 sequentialSort + the merge cascade fmi.cpp:220-257).
 // Only the low `bits` bits are sorted.  The result is in `d_keys` or `d_alt`; returns which.
@@ -671,14 +695,14 @@ msd_tile_scan(unsigned int* __restrict__ tiles, uint64_t entries)
 
 // The partition pass: keys of a tile go to their buckets in `out`, in any order within a bucket.
 template<class KeyT>
-__global__ void __launch_bounds__(MSD_THREADS)
+__global__ void __launch_bounds__(MSD_THREADS, 3)
 msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned long long* __restrict__ bounds,
             const unsigned int* __restrict__ tile_first, unsigned int segments, int shift, unsigned int bins,
             unsigned long long* __restrict__ cursors)
 {
   extern __shared__ __align__(16) unsigned char msd_shared[];
   KeyT* staged = reinterpret_cast<KeyT*>(msd_shared);   // MSD_TILE keys
-  __shared__ unsigned int histogram[MSD_MAX_BINS];      // count, then the bin's first slot in `staged`
+  __shared__ unsigned int histogram[MSD_MAX_BINS];      // count, then the bin's next free slot in `staged`
   __shared__ unsigned long long target[MSD_MAX_BINS];   // output index of the bin's first key minus its first slot
   __shared__ unsigned int warp_totals[MSD_THREADS / 32];
   __shared__ unsigned int s_segment; __shared__ unsigned long long s_begin, s_end; __shared__ int s_valid;
@@ -695,7 +719,7 @@ msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned 
   const unsigned int count = (unsigned int)(s_end - s_begin), mask = bins - 1;
   const unsigned int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-  KeyT keys[MSD_ITEMS]; unsigned int rank[MSD_ITEMS];
+  KeyT keys[MSD_ITEMS];
 #pragma unroll
   for(int i = 0; i < MSD_ITEMS; i++)
   {
@@ -706,7 +730,7 @@ msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned 
   for(int i = 0; i < MSD_ITEMS; i++)
   {
     unsigned int k = threadIdx.x + i * MSD_THREADS;
-    rank[i] = (k < count ? atomicAdd(&histogram[(unsigned int)(keys[i] >> shift) & mask], 1u) : 0u);
+    if(k < count) { atomicAdd(&histogram[(unsigned int)(keys[i] >> shift) & mask], 1u); }
   }
   __syncthreads();
 
@@ -746,7 +770,7 @@ msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned 
   for(int i = 0; i < MSD_ITEMS; i++)
   {
     unsigned int k = threadIdx.x + i * MSD_THREADS;
-    if(k < count) { staged[histogram[(unsigned int)(keys[i] >> shift) & mask] + rank[i]] = keys[i]; }
+    if(k < count) { staged[atomicAdd(&histogram[(unsigned int)(keys[i] >> shift) & mask], 1u)] = keys[i]; }   // the bin's next slot
   }
   __syncthreads();
   for(unsigned int k = threadIdx.x; k < count; k += MSD_THREADS)
@@ -759,13 +783,21 @@ msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned 
 // Partitions keys[0, n) by the bits [low_bit, high_bit) with one or two MSD passes (at most 20 bits). On return
 // *where holds the partitioned keys (d_keys or d_alt) and d_offsets[r] (r = 0 .. 2^(high_bit - low_bit)) is the index
 // of the first key whose bits are >= r: the ranges of the counting pass.
-template<class KeyT>
-static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int high_bit, unsigned long long* d_offsets,
-                         KeyT** where, cudaStream_t stream)
+static void msd_geometry(int low_bit, int high_bit, int* levels, int* bits1, int* bits2)
 {
   const int total_bits = high_bit - low_bit;
-  const int levels = (total_bits > 10 ? 2 : 1);
-  const int bits1 = (levels == 1 ? total_bits : (total_bits + 1) / 2), bits2 = total_bits - bits1;
+  *levels = (total_bits > 10 ? 2 : 1);
+  *bits1 = (*levels == 1 ? total_bits : (total_bits + 1) / 2);
+  *bits2 = total_bits - *bits1;
+}
+
+template<class KeyT>
+static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int high_bit, unsigned long long* d_offsets,
+                         KeyT** where, cudaStream_t stream, const unsigned long long* level1_counts)
+{
+  const int total_bits = high_bit - low_bit;
+  int levels = 1, bits1 = total_bits, bits2 = 0;
+  msd_geometry(low_bit, high_bit, &levels, &bits1, &bits2);
   const unsigned int bins1 = 1u << bits1, bins2 = 1u << bits2;
   const uint64_t ranges = 1ull << total_bits;
 
@@ -779,13 +811,20 @@ static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int
   const unsigned int host_tiles[2] = { 0, tiles_level1 };
   BWTM_CUDA(cudaMemcpyAsync(bounds1.ptr, host_bounds, sizeof(host_bounds), cudaMemcpyHostToDevice, stream));
   BWTM_CUDA(cudaMemcpyAsync(tiles1.ptr, host_tiles, sizeof(host_tiles), cudaMemcpyHostToDevice, stream));
-  BWTM_CUDA(cudaMemsetAsync(counts1.ptr, 0, bins1 * sizeof(unsigned long long), stream));
 
-  // level 1 (the most significant bits)
+  // level 1 (the most significant bits); its histogram may have been collected by the walk
   const int shift1 = low_bit + bits2;
-  msd_histogram<KeyT><<<tiles_level1, MSD_THREADS, 0, stream>>>(d_keys, bounds1.as<unsigned long long>(), tiles1.as<unsigned int>(), 1, shift1, bins1,
-                                                                 counts1.as<unsigned long long>());
-  BWTM_LAUNCH_CHECK();
+  if(level1_counts != nullptr)
+  {
+    BWTM_CUDA(cudaMemcpyAsync(counts1.ptr, level1_counts, bins1 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
+  }
+  else
+  {
+    BWTM_CUDA(cudaMemsetAsync(counts1.ptr, 0, bins1 * sizeof(unsigned long long), stream));
+    msd_histogram<KeyT><<<tiles_level1, MSD_THREADS, 0, stream>>>(d_keys, bounds1.as<unsigned long long>(), tiles1.as<unsigned int>(), 1, shift1, bins1,
+                                                                   counts1.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+  }
   unsigned long long* level1_bounds = (levels == 1 ? d_offsets : bounds2.as<unsigned long long>());
   msd_cursors<<<1, std::max(32u, bins1), 0, stream>>>(counts1.as<unsigned long long>(), bounds1.as<unsigned long long>(), bins1,
                                                       cursors1.as<unsigned long long>(), level1_bounds, tiles2.as<unsigned int>());
@@ -825,26 +864,60 @@ static uint64_t env_number(const char* name, uint64_t fallback)
   return (text == nullptr ? fallback : (uint64_t)strtoull(text, nullptr, 10));
 }
 
-template<class KeyT>
-int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit)
+// How sort_keys treats n keys of `bits` bits below key_limit: plain radix sort of everything, or the high bits
+// partitioned / radix-sorted and the low `local_bits` bits counted range by range.
+struct SortPlan
 {
+  bool     counting;      // the counting route
+  bool     msd;           // ... with MSD partition passes for the high bits
+  int      local_bits;
+  uint64_t key_limit;
+};
+
+static SortPlan sort_plan(uint64_t n, int bits, uint64_t key_limit)
+{
+  SortPlan plan;
   if(key_limit == 0 || (bits < 64 && key_limit > (1ull << bits))) { key_limit = (bits < 64 ? 1ull << bits : ~0ull); }
-  cub::DoubleBuffer<KeyT> buffers(d_keys, d_alt);
-  // BWTM_LOCAL_SORT_MIN: smallest input that takes the counting route (tests force it with 1);
-  // BWTM_LOCAL_SORT_LIMIT: most keys one range may hold before the plain radix sort takes over.
+  plan.key_limit = key_limit;
+  // BWTM_LOCAL_SORT_MIN: smallest input that takes the counting route (tests force it with 1).
   const uint64_t local_min = env_number("BWTM_LOCAL_SORT_MIN", 1ull << 22);
-  const uint64_t local_limit = env_number("BWTM_LOCAL_SORT_LIMIT", 1ull << 19);
-  const uint64_t small_keys = std::min<uint64_t>(env_number("BWTM_LOCAL_SORT_SMALL", SMALL_RANGE_KEYS), SMALL_RANGE_KEYS);   // tests: 0
-  const int local_bits = std::min(15, std::max(12, bits - 16));
+  plan.local_bits = std::min(15, std::max(12, bits - 16));
+  const int local_bits = plan.local_bits;
   // The counting pass costs about the same per range whatever the range holds: it pays off when the ranges
   // are well filled (a rank of a multi-GPU merge sorts only its share of the keys over the same positions).
   const uint64_t expected_ranges = (bits > local_bits ? std::min<uint64_t>(1ull << std::min(bits - local_bits, 40), ((key_limit - 1) >> local_bits) + 1) : 1);
   const uint64_t local_density = env_number("BWTM_LOCAL_SORT_DENSITY", 8192);
   const uint64_t max_density = env_number("BWTM_LOCAL_SORT_MAX_DENSITY", 1ull << 19);   // 0: no upper bound (tests)
-  if(n < local_min || bits <= local_bits || bits - local_bits > 22 || n / expected_ranges < local_density ||
-     (max_density > 0 && n / expected_ranges > max_density))   // nearly every range would be a heavy one (a small A under a large B)
+  plan.counting = !(n < local_min || bits <= local_bits || bits - local_bits > 22 || n / expected_ranges < local_density ||
+                    (max_density > 0 && n / expected_ranges > max_density));   // nearly every range would be a heavy one (a small A under a large B)
+  plan.msd = (plan.counting && bits - local_bits <= 20 && env_number("BWTM_MSD", 1) != 0);
+  return plan;
+}
+
+bool sort_plan_level1(uint64_t n, int bits, uint64_t key_limit, int* shift, unsigned int* bins)
+{
+  SortPlan plan = sort_plan(n, bits, key_limit);
+  if(!plan.msd) { return false; }
+  int levels = 1, bits1 = 0, bits2 = 0;
+  msd_geometry(plan.local_bits, bits, &levels, &bits1, &bits2);
+  *shift = plan.local_bits + bits2; *bins = 1u << bits1;
+  return true;
+}
+
+template<class KeyT>
+int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit,
+              const unsigned long long* level1_counts)
+{
+  const SortPlan plan = sort_plan(n, bits, key_limit);
+  key_limit = plan.key_limit;
+  cub::DoubleBuffer<KeyT> buffers(d_keys, d_alt);
+  // BWTM_LOCAL_SORT_LIMIT: most keys one range may hold before the plain radix sort takes over.
+  const uint64_t local_limit = env_number("BWTM_LOCAL_SORT_LIMIT", 1ull << 19);
+  const uint64_t small_keys = std::min<uint64_t>(env_number("BWTM_LOCAL_SORT_SMALL", SMALL_RANGE_KEYS), SMALL_RANGE_KEYS);   // tests: 0
+  const int local_bits = plan.local_bits;
+  if(!plan.counting)
   {
-    BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
+  BWTM_TRY(radix_sort_bits<KeyT>(buffers, n, 0, bits, stream));
     *sorted = buffers.Current();
     return BWTM_OK;
   }
@@ -855,10 +928,10 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   BWTM_CUDA(cudaMemsetAsync(heavy.ptr, 0, (2 + 2 * MAX_HEAVY_RANGES) * sizeof(unsigned long long), stream));
   // The high bits: MSD partition passes (they also deliver the range offsets), or the library's radix passes
   // (BWTM_MSD=0, and keys with more than 20 high bits).
-  if(bits - local_bits <= 20 && env_number("BWTM_MSD", 1) != 0)
+  if(plan.msd)
   {
     KeyT* where = nullptr;
-    BWTM_TRY(msd_partition<KeyT>(d_keys, d_alt, n, local_bits, bits, offsets.as<unsigned long long>(), &where, stream));
+    BWTM_TRY(msd_partition<KeyT>(d_keys, d_alt, n, local_bits, bits, offsets.as<unsigned long long>(), &where, stream, level1_counts));
     if(where != buffers.Current()) { buffers.selector ^= 1; }
   }
   else
@@ -908,7 +981,7 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   return BWTM_OK;
 }
 
-template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t, uint64_t);
-template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t, uint64_t);
+template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t, uint64_t, const unsigned long long*);
+template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t, uint64_t, const unsigned long long*);
 
 } // namespace bwtm
