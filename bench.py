@@ -429,6 +429,7 @@ def main():
         torch.cuda.profiler.start()
     ms_total = 0.0
     step_ms_device = []
+    memory_before = bwtm_b200.memory_stats(reset_peak=True)[0]
     for _ in range(args.steps):
         if flush is not None:
             flush.fill_(1); torch.cuda.synchronize()
@@ -444,6 +445,7 @@ def main():
         merged_bytes = M.bytes()
         M.close()
     barrier()
+    memory_peak = bwtm_b200.memory_stats()[1]
     if profiling:
         torch.cuda.profiler.stop()
     clocks = sampler.stop()
@@ -577,6 +579,8 @@ def main():
                  "note": "pair records of both inputs built once before the timed region (bwtm_index_build_pairs), like K0; "
                          "e2e builds them inside its timed region" if pair_build_ms is not None else "single-step walk"},
         "verified": verified,
+        "device_memory": {"inputs_resident_bytes": int(memory_before), "peak_bytes_during_merge": int(memory_peak),
+                          "work_bytes": int(memory_peak - memory_before)},
         "stages_ms": {k: v * 1e3 for k, v in stage.items()},
         "stage_bases_per_second": {k: (n_b / v if v > 0 else None) for k, v in stage.items()},
         "ra_runs": last["ra_runs"], "merged_runs": last["merged_runs"],

@@ -24,7 +24,7 @@ ERROR_NAMES = {-1: "BWTM_ERR_ARGUMENT", -2: "BWTM_ERR_CUDA", -3: "BWTM_ERR_MEMOR
 
 # Every symbol include/bwtm.h declares.
 EXPORTS = [
-    "bwtm_last_error", "bwtm_version", "bwtm_device_count", "bwtm_set_device", "bwtm_kernel_launches",
+    "bwtm_last_error", "bwtm_version", "bwtm_device_count", "bwtm_set_device", "bwtm_kernel_launches", "bwtm_memory_stats",
     "bwtm_index_create", "bwtm_index_create_pair", "bwtm_index_create_device", "bwtm_index_create_plain", "bwtm_index_create_runs", "bwtm_index_destroy", "bwtm_index_get_info",
     "bwtm_index_download", "bwtm_index_samples", "bwtm_index_extract", "bwtm_index_hash",
     "bwtm_index_build_pairs", "bwtm_rank", "bwtm_lf", "bwtm_lf2", "bwtm_count", "bwtm_merge", "bwtm_rank_array",
@@ -94,6 +94,7 @@ def lib():
     L.bwtm_device_count.argtypes = [C.POINTER(C.c_int)]
     L.bwtm_set_device.argtypes = [C.c_int]
     L.bwtm_kernel_launches.restype = C.c_uint64
+    L.bwtm_memory_stats.argtypes = [u64p, u64p, C.c_int]
     L.bwtm_index_create.argtypes = [u8p, C.c_uint64, u64p, C.POINTER(vp)]
     L.bwtm_index_create_pair.argtypes = [u8p, C.c_uint64, u64p, u8p, C.c_uint64, u64p, C.POINTER(vp), C.POINTER(vp)]
     L.bwtm_index_create_device.argtypes = [vp, C.c_uint64, C.POINTER(vp)]
@@ -137,6 +138,13 @@ def _p(a, t):
 
 def kernel_launches():
     return lib().bwtm_kernel_launches()
+
+
+def memory_stats(reset_peak=False):
+    """(bytes in use, peak bytes since the last reset) of the library's device allocations."""
+    used = C.c_uint64(0); peak = C.c_uint64(0)
+    check(lib().bwtm_memory_stats(C.byref(used), C.byref(peak), 1 if reset_peak else 0))
+    return used.value, peak.value
 
 
 def set_device(device):

@@ -719,6 +719,21 @@ int bwtm_index_create_pair(const uint8_t* rle_a, uint64_t rle_bytes_a, const uin
   return BWTM_OK;
 }
 
+// Bytes of the library's memory pool in use now and at their highest since the last reset.
+int bwtm_memory_stats(uint64_t* used_bytes, uint64_t* peak_bytes, int reset_peak)
+{
+  int device = 0; cudaMemPool_t pool;
+  BWTM_CUDA(cudaGetDevice(&device));
+  BWTM_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+  uint64_t used = 0, peak = 0;
+  BWTM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
+  BWTM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &peak));
+  if(used_bytes != nullptr) { *used_bytes = used; }
+  if(peak_bytes != nullptr) { *peak_bytes = peak; }
+  if(reset_peak) { uint64_t zero = 0; BWTM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero)); }
+  return BWTM_OK;
+}
+
 int bwtm_index_destroy(bwtm_index* index)
 {
   index_free(index);

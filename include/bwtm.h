@@ -124,6 +124,10 @@ int bwtm_device_count(int* count);
 int bwtm_set_device(int device);
 /* Kernels launched by this library in this process so far (bench.py's gpu_launches). */
 uint64_t bwtm_kernel_launches(void);
+/* Device memory held by the library's allocations on the current device (indexes, work buffers): bytes in use now and
+   their highest value since the last reset (reset_peak != 0 restarts the high-water mark at the current use). The
+   counterpart of the reference's memoryUsage() report lines (fmi.cpp:348,363; utils.cpp:98-110). */
+int bwtm_memory_stats(uint64_t* used_bytes, uint64_t* peak_bytes, int reset_peak);
 
 /*----------------------------------------------------------------------------*/
 /* Index: replaces BWT::build (bwt.cpp:476-512) and BWT::setHeader (bwt.cpp:468-474). */
