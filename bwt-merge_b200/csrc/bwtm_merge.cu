@@ -1541,13 +1541,16 @@ static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* op
   KeyT* sorted = nullptr;
   {
     // The first partition level of the sort needs the histogram of its digit: the walk counts it while it writes.
-    WalkHistogram histogram = { nullptr, 0, 1 };
+    WalkHistogram histogram = { nullptr, 0, 1, nullptr, 0 };
     DeviceBuffer digit_counts;
-    if(sort_plan_level1(n_b, bit_length_host(a->size), a->size + 1, &histogram.shift, &histogram.bins))
+    uint64_t fine_bins = 0;
+    if(sort_plan_histogram(n_b, bit_length_host(a->size), a->size + 1, &histogram, &fine_bins))
     {
-      BWTM_TRY(digit_counts.allocate(histogram.bins * sizeof(unsigned long long)));
-      BWTM_CUDA(cudaMemsetAsync(digit_counts.ptr, 0, histogram.bins * sizeof(unsigned long long), stream));
-      histogram.counts = digit_counts.as<unsigned long long>();
+      const uint64_t counters = (fine_bins > 0 ? fine_bins : histogram.bins);
+      BWTM_TRY(digit_counts.allocate(counters * sizeof(unsigned long long)));
+      BWTM_CUDA(cudaMemsetAsync(digit_counts.ptr, 0, counters * sizeof(unsigned long long), stream));
+      if(fine_bins > 0) { histogram.fine_counts = digit_counts.as<unsigned long long>(); }
+      else { histogram.counts = digit_counts.as<unsigned long long>(); }
     }
     timer.start();
     uint64_t emitted = 0;
@@ -1562,7 +1565,7 @@ static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* op
     }
     timings->ra_values = emitted;
     timer.start();
-    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream, a->size + 1, histogram.counts));
+    BWTM_TRY(sort_keys<KeyT>(keys.as<KeyT>(), alt.as<KeyT>(), n_b, bit_length_host(a->size), &sorted, stream, a->size + 1, &histogram));
     timings->sort_seconds = timer.stop() * 1e-3;
   }
   if(sorted == keys.as<KeyT>()) { alt.release(); } else { keys.release(); }

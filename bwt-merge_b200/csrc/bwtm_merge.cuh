@@ -13,6 +13,10 @@ struct WalkHistogram
   unsigned long long* counts;   // bins zeroed counters on the device, or null
   int                 shift;
   unsigned int        bins;     // power of two, at most 1024
+  // Alternatively the histogram of ALL the partitioned bits, counted with global reductions (the walk waits for DRAM,
+  // its L2 has atomic throughput to spare): fine_counts[value >> fine_shift] += 1. Then `counts` is not used.
+  unsigned long long* fine_counts;
+  int                 fine_shift;
 };
 
 // K1. Appends one RA value per suffix of the sequences [seq_first, seq_last] of b to d_out (unordered).
@@ -42,10 +46,10 @@ int walk_counters_check(const void* host_copy);   // non-zero: the output buffer
 // K2. Radix sort on the low `bits` bits; *sorted points into d_keys or d_alt.
 template<class KeyT>
 int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit = 0,   // key_limit: exclusive bound of the key values, when known
-              const unsigned long long* level1_counts = nullptr);   // histogram delivered by the walk (sort_plan_level1)
-// True when sort_keys(n, bits, key_limit) partitions the high bits itself; then (shift, bins) describe the digit of its
-// first level, whose histogram the walk can deliver.
-bool sort_plan_level1(uint64_t n, int bits, uint64_t key_limit, int* shift, unsigned int* bins);
+              const WalkHistogram* walked = nullptr);   // histogram delivered by the walk (sort_plan_histogram)
+// True when sort_keys(n, bits, key_limit) partitions the high bits itself; then `plan` describes the histogram the walk
+// can deliver (counts / fine_counts are left null: the caller allocates bins, or *fine_bins, zeroed counters).
+bool sort_plan_histogram(uint64_t n, int bits, uint64_t key_limit, WalkHistogram* plan, uint64_t* fine_bins);
 
 // Sequential state of the byte encoder that crosses slabs (and GPU slices).
 struct EncodeControl

@@ -466,7 +466,7 @@ k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
   for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = (PosT)a.C[c]; } }
   for(unsigned int d = threadIdx.x; d < 1024; d += PW_THREADS) { digit_counts[d] = 0; }
   __syncthreads();
-  const bool counting = (histogram.counts != nullptr);
+  const bool counting = (histogram.counts != nullptr), counting_fine = (histogram.fine_counts != nullptr);
   const unsigned int digit_mask = histogram.bins - 1;
 
   const unsigned FULL = 0xFFFFFFFFu;
@@ -533,6 +533,7 @@ k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
           KeyT value = stage[k];
           out[base + k] = value;
           if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+          if(counting_fine) { atomicAdd(histogram.fine_counts + (uint64_t)(value >> histogram.fine_shift), 1ull); }
         }
       }
       else
@@ -637,6 +638,7 @@ k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
           KeyT value = stage[k];
           out[base + k] = value;
           if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+          if(counting_fine) { atomicAdd(histogram.fine_counts + (uint64_t)(value >> histogram.fine_shift), 1ull); }
         }
     }
     else if(lane == 0) { counters->overflow = 1; }
@@ -673,8 +675,8 @@ int walk_pairs_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_firs
                      KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, cudaStream_t stream,
                      const WalkHistogram* histogram)
 {
-  WalkHistogram counting = { nullptr, 0, 1 };
-  if(histogram != nullptr && histogram->counts != nullptr && histogram->bins <= 1024) { counting = *histogram; }
+  WalkHistogram counting = { nullptr, 0, 1, nullptr, 0 };
+  if(histogram != nullptr && (histogram->fine_counts != nullptr || (histogram->counts != nullptr && histogram->bins <= 1024))) { counting = *histogram; if(counting.counts == nullptr) { counting.bins = 1; } }
   static_assert(sizeof(PairWalkCounters) == 24, "counter layout shared with the single-step walk");
   if(a->d_pairs == nullptr || b->d_pairs == nullptr) { set_error("pair records missing"); return BWTM_ERR_INTERNAL; }
   int device = 0, sms = 0;

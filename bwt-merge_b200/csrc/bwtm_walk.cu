@@ -85,7 +85,7 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
   for(int c = 0; c <= SIGMA; c++) { if(threadIdx.x == c) { c_a[c] = (PosT)a.C[c]; c_b[c] = (PosT)b.C[c]; } }
   for(unsigned int d = threadIdx.x; d < 1024; d += WALK_THREADS) { digit_counts[d] = 0; }
   __syncthreads();
-  const bool counting = (histogram.counts != nullptr);
+  const bool counting = (histogram.counts != nullptr), counting_fine = (histogram.fine_counts != nullptr);
   const unsigned int digit_mask = histogram.bins - 1;
 
   const unsigned FULL = 0xFFFFFFFFu;
@@ -149,6 +149,7 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
           KeyT value = stage[k];
           out[base + k] = value;
           if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+          if(counting_fine) { atomicAdd(histogram.fine_counts + (uint64_t)(value >> histogram.fine_shift), 1ull); }
         }
       }
       else
@@ -192,6 +193,7 @@ k1_walk_coop(DeviceIndex a, DeviceIndex b, uint64_t seq_begin, uint64_t seq_end,
           KeyT value = stage[k];
           out[base + k] = value;
           if(counting) { atomicAdd(&digit_counts[(unsigned int)(value >> histogram.shift) & digit_mask], 1u); }
+          if(counting_fine) { atomicAdd(histogram.fine_counts + (uint64_t)(value >> histogram.fine_shift), 1ull); }
         }
     }
     else if(lane == 0) { counters->overflow = 1; }
@@ -229,8 +231,8 @@ int walk_sequences_async(const bwtm_index* a, const bwtm_index* b, uint64_t seq_
                          KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor,
                          int max_blocks_per_sm, cudaStream_t stream, const WalkHistogram* histogram)
 {
-  WalkHistogram counting = { nullptr, 0, 1 };
-  if(histogram != nullptr && histogram->counts != nullptr && histogram->bins <= 1024) { counting = *histogram; }
+  WalkHistogram counting = { nullptr, 0, 1, nullptr, 0 };
+  if(histogram != nullptr && (histogram->fine_counts != nullptr || (histogram->counts != nullptr && histogram->bins <= 1024))) { counting = *histogram; if(counting.counts == nullptr) { counting.bins = 1; } }
   int device = 0, sms = 0;
   BWTM_CUDA(cudaGetDevice(&device));
   BWTM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
@@ -783,6 +785,25 @@ msd_scatter(const KeyT* __restrict__ in, KeyT* __restrict__ out, const unsigned 
 // Partitions keys[0, n) by the bits [low_bit, high_bit) with one or two MSD passes (at most 20 bits). On return
 // *where holds the partitioned keys (d_keys or d_alt) and d_offsets[r] (r = 0 .. 2^(high_bit - low_bit)) is the index
 // of the first key whose bits are >= r: the ranges of the counting pass.
+// sums[row] = sum of the `width` counters of a row (level-1 counts from the histogram of all partitioned bits).
+__global__ void __launch_bounds__(256)
+msd_row_sums(const unsigned long long* __restrict__ fine, unsigned int width, unsigned long long* __restrict__ sums)
+{
+  __shared__ unsigned long long warp_totals[8];
+  unsigned long long mine = 0;
+  for(unsigned int d = threadIdx.x; d < width; d += 256) { mine += fine[(uint64_t)blockIdx.x * width + d]; }
+#pragma unroll
+  for(int offset = 16; offset > 0; offset >>= 1) { mine += __shfl_xor_sync(0xFFFFFFFFu, mine, offset); }
+  if((threadIdx.x & 31) == 0) { warp_totals[threadIdx.x >> 5] = mine; }
+  __syncthreads();
+  if(threadIdx.x == 0)
+  {
+    unsigned long long total = 0;
+    for(int w = 0; w < 8; w++) { total += warp_totals[w]; }
+    sums[blockIdx.x] = total;
+  }
+}
+
 static void msd_geometry(int low_bit, int high_bit, int* levels, int* bits1, int* bits2)
 {
   const int total_bits = high_bit - low_bit;
@@ -793,8 +814,10 @@ static void msd_geometry(int low_bit, int high_bit, int* levels, int* bits1, int
 
 template<class KeyT>
 static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int high_bit, unsigned long long* d_offsets,
-                         KeyT** where, cudaStream_t stream, const unsigned long long* level1_counts)
+                         KeyT** where, cudaStream_t stream, const WalkHistogram* walked)
 {
+  const unsigned long long* level1_counts = (walked != nullptr ? walked->counts : nullptr);
+  const unsigned long long* fine_counts = (walked != nullptr ? walked->fine_counts : nullptr);
   const int total_bits = high_bit - low_bit;
   int levels = 1, bits1 = total_bits, bits2 = 0;
   msd_geometry(low_bit, high_bit, &levels, &bits1, &bits2);
@@ -814,7 +837,12 @@ static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int
 
   // level 1 (the most significant bits); its histogram may have been collected by the walk
   const int shift1 = low_bit + bits2;
-  if(level1_counts != nullptr)
+  if(fine_counts != nullptr)   // all partitioned bits were counted by the walk: level 1 is the sum of its rows
+  {
+    msd_row_sums<<<bins1, 256, 0, stream>>>(fine_counts, bins2, counts1.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+  }
+  else if(level1_counts != nullptr)
   {
     BWTM_CUDA(cudaMemcpyAsync(counts1.ptr, level1_counts, bins1 * sizeof(unsigned long long), cudaMemcpyDeviceToDevice, stream));
   }
@@ -839,16 +867,21 @@ static int msd_partition(KeyT* d_keys, KeyT* d_alt, uint64_t n, int low_bit, int
   // level 2: every bucket of level 1 is a segment
   msd_tile_scan<<<1, 1024, 0, stream>>>(tiles2.as<unsigned int>(), bins1);
   BWTM_LAUNCH_CHECK();
-  BWTM_TRY(counts2.allocate(ranges * sizeof(unsigned long long)));
-  BWTM_CUDA(cudaMemsetAsync(counts2.ptr, 0, ranges * sizeof(unsigned long long), stream));
   const unsigned int tiles_level2 = tiles_level1 + bins1;   // upper bound: every segment wastes less than one tile
-  msd_histogram<KeyT><<<tiles_level2, MSD_THREADS, 0, stream>>>(d_alt, bounds2.as<unsigned long long>(), tiles2.as<unsigned int>(), bins1, low_bit, bins2,
-                                                                 counts2.as<unsigned long long>());
-  BWTM_LAUNCH_CHECK();
+  const unsigned long long* level2_counts = fine_counts;
+  if(level2_counts == nullptr)
+  {
+    BWTM_TRY(counts2.allocate(ranges * sizeof(unsigned long long)));
+    BWTM_CUDA(cudaMemsetAsync(counts2.ptr, 0, ranges * sizeof(unsigned long long), stream));
+    msd_histogram<KeyT><<<tiles_level2, MSD_THREADS, 0, stream>>>(d_alt, bounds2.as<unsigned long long>(), tiles2.as<unsigned int>(), bins1, low_bit, bins2,
+                                                                   counts2.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+    level2_counts = counts2.as<unsigned long long>();
+  }
   // The cursors of level 2 are written over the counts; their initial values are the range offsets.
   DeviceBuffer cursors2, unused_tiles;
   BWTM_TRY(cursors2.allocate(ranges * sizeof(unsigned long long))); BWTM_TRY(unused_tiles.allocate((ranges + 1) * sizeof(unsigned int)));
-  msd_cursors<<<bins1, std::max(32u, bins2), 0, stream>>>(counts2.as<unsigned long long>(), bounds2.as<unsigned long long>(), bins2,
+  msd_cursors<<<bins1, std::max(32u, bins2), 0, stream>>>(level2_counts, bounds2.as<unsigned long long>(), bins2,
                                                           cursors2.as<unsigned long long>(), d_offsets, unused_tiles.as<unsigned int>());
   BWTM_LAUNCH_CHECK();
   msd_scatter<KeyT><<<tiles_level2, MSD_THREADS, staged_bytes, stream>>>(d_alt, d_keys, bounds2.as<unsigned long long>(), tiles2.as<unsigned int>(), bins1, low_bit, bins2,
@@ -894,19 +927,23 @@ static SortPlan sort_plan(uint64_t n, int bits, uint64_t key_limit)
   return plan;
 }
 
-bool sort_plan_level1(uint64_t n, int bits, uint64_t key_limit, int* shift, unsigned int* bins)
+bool sort_plan_histogram(uint64_t n, int bits, uint64_t key_limit, WalkHistogram* histogram, uint64_t* fine_bins)
 {
   SortPlan plan = sort_plan(n, bits, key_limit);
+  histogram->counts = nullptr; histogram->fine_counts = nullptr; histogram->shift = 0; histogram->bins = 1; histogram->fine_shift = 0;
+  *fine_bins = 0;
   if(!plan.msd) { return false; }
   int levels = 1, bits1 = 0, bits2 = 0;
   msd_geometry(plan.local_bits, bits, &levels, &bits1, &bits2);
-  *shift = plan.local_bits + bits2; *bins = 1u << bits1;
+  histogram->shift = plan.local_bits + bits2; histogram->bins = 1u << bits1;
+  // BWTM_FINE_HISTOGRAM=0: only the first level's digit is counted by the walk (in shared memory).
+  if(levels == 2 && env_number("BWTM_FINE_HISTOGRAM", 1) != 0) { histogram->fine_shift = plan.local_bits; *fine_bins = 1ull << (bits - plan.local_bits); }
   return true;
 }
 
 template<class KeyT>
 int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cudaStream_t stream, uint64_t key_limit,
-              const unsigned long long* level1_counts)
+              const WalkHistogram* walked)
 {
   const SortPlan plan = sort_plan(n, bits, key_limit);
   key_limit = plan.key_limit;
@@ -931,7 +968,7 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   if(plan.msd)
   {
     KeyT* where = nullptr;
-    BWTM_TRY(msd_partition<KeyT>(d_keys, d_alt, n, local_bits, bits, offsets.as<unsigned long long>(), &where, stream, level1_counts));
+    BWTM_TRY(msd_partition<KeyT>(d_keys, d_alt, n, local_bits, bits, offsets.as<unsigned long long>(), &where, stream, walked));
     if(where != buffers.Current()) { buffers.selector ^= 1; }
   }
   else
@@ -981,7 +1018,7 @@ int sort_keys(KeyT* d_keys, KeyT* d_alt, uint64_t n, int bits, KeyT** sorted, cu
   return BWTM_OK;
 }
 
-template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t, uint64_t, const unsigned long long*);
-template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t, uint64_t, const unsigned long long*);
+template int sort_keys<uint32_t>(uint32_t*, uint32_t*, uint64_t, int, uint32_t**, cudaStream_t, uint64_t, const WalkHistogram*);
+template int sort_keys<uint64_t>(uint64_t*, uint64_t*, uint64_t, int, uint64_t**, cudaStream_t, uint64_t, const WalkHistogram*);
 
 } // namespace bwtm
