@@ -190,6 +190,18 @@ static int agree_on_status(bwtm_comm* comm, int rc, cudaStream_t stream, const c
   return (int)all;
 }
 
+// Fault injection for the tests of the above: BWTM_INJECT_FAILURE=<phase>:<rank> makes that rank fail locally in that
+// phase ("search", "interleave" or "writer"), as an allocation failure would.
+static int injected_failure(const char* phase, int rank)
+{
+  const char* spec = getenv("BWTM_INJECT_FAILURE");
+  if(spec == nullptr) { return BWTM_OK; }
+  size_t length = strlen(phase);
+  if(strncmp(spec, phase, length) != 0 || spec[length] != ':' || atoi(spec + length + 1) != rank) { return BWTM_OK; }
+  set_error("injected failure in phase '%s' on rank %d", phase, rank);
+  return BWTM_ERR_MEMORY;
+}
+
 static void window_close(bwtm_comm* comm, PeerWindow* window)
 {
   for(int p = 0; p < (int)window->mapped.size(); p++)
@@ -317,6 +329,7 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   KeyT* sorted = nullptr;
   auto search_and_sort = [&]() -> int
   {
+    BWTM_TRY(injected_failure("search", r));
     // Every rank walks 1/G of b's sequences but would build the pair records of all of a and b: the two-step walk is
     // chosen as on one GPU, with the inserted share in place of |b|.
     BWTM_TRY(prepare_walk(a, b, (uint64_t)((double)n_b * ((double)seq_count / (double)m_b)), stream, timings));
@@ -519,6 +532,7 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   auto interleave_slabs = [&]() -> int
   {
     BWTM_TRY(merge_rc);
+    BWTM_TRY(injected_failure("interleave", r));
     BWTM_TRY(control.allocate(sizeof(EncodeControl)));
     if(!parallel) { return BWTM_OK; }
     BWTM_TRY(tile_j.allocate((slab / interleave_tile_size() + 2) * sizeof(uint64_t)));
@@ -557,6 +571,7 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   int rc = BWTM_OK;
   if(upstream_failed) { set_error("an earlier rank of the writer chain failed"); rc = BWTM_ERR_COMM; }
   else { rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream); }
+  if(rc == BWTM_OK) { rc = injected_failure("writer", r); }
   timer.start();
   if(rc == BWTM_OK && slice > 0)
   {

@@ -31,11 +31,30 @@ def main():
             comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
         check_cases(comm, rank, thr, todo)
     os.environ.pop("BWTM_NCCL_EXCHANGE", None)
+    check_failures(comm, rank, world, thr)
     dist.barrier()
     if rank == 0:
         print("dist_check ok: %d ranks, %d cases" % (world, sum(len(todo) for _, todo in runs)))
     comm.close()
     dist.destroy_process_group()
+
+
+def check_failures(comm, rank, world, thr):
+    """A rank that fails locally must not leave the others waiting: every rank gets an error from the same merge, and the
+    communicator is still usable afterwards (bwtm_dist.cu: agree_on_status, poisoned writer state)."""
+    A = FMI.synthetic(50000, 42, 60, thr, [(1, 3000)]); B = FMI.synthetic(50000, 42, 60, thr, [(2, 1500)])
+    want = FMI.merge(A, B, keep_inputs=True).rle()
+    for phase in ("search", "interleave", "writer"):
+        for failing in sorted({0, world - 1, world // 2}):
+            os.environ["BWTM_INJECT_FAILURE"] = "%s:%d" % (phase, failing)
+            try:
+                comm.merge(A, B, keep_inputs=True)
+                raise AssertionError("rank %d: the merge succeeded although rank %d failed in '%s'" % (rank, failing, phase))
+            except bwtm_b200.BwtmError as error:
+                assert ("injected" in str(error)) == (rank == failing) or "failed" in str(error), str(error)
+            finally:
+                os.environ.pop("BWTM_INJECT_FAILURE", None)
+            assert np.array_equal(comm.merge(A, B, keep_inputs=True).rle(), want), "rank %d: merge after a failed merge differs" % rank
 
 
 def check_cases(comm, rank, thr, cases):
