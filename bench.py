@@ -382,8 +382,11 @@ def main():
     # ---- verification (outside the timed region): the first merge against the reference's result ----------------
     verified = None
     args.warmup = max(1, args.warmup)
+    warmup_ms = []
     for it in range(args.warmup):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
         M = one_merge()
+        torch.cuda.synchronize(); warmup_ms.append(round((time.perf_counter() - t0) * 1e3, 2))
         if it == 0 and not args.no_verify and rank == 0:
             got = M.rle()
             digest = hashlib.sha256(got.tobytes()).hexdigest()
@@ -573,6 +576,7 @@ def main():
         "dtype": "u64", "data": "synthetic",
         "config": config_dict(args, n_a, n_b, [info_a.rle_bytes, info_b.rle_bytes, merged_bytes]),
         "input_build_seconds": t_build, "steps_ms": [round(x, 2) for x in step_ms_device],
+        "warmup_ms": warmup_ms,    # host wall clock of the untimed warm-up merges: the first one pays for the memory pools' growth
         "walk": {"record_bytes": int(last["walk_record_bytes"]), "table_bytes": int(last["walk_table_bytes"]),
                  "search_batches": int(last["search_batches"]),
                  "pair_records_build_ms": pair_build_ms,

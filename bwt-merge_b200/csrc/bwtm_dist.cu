@@ -110,9 +110,11 @@ struct bwtm_comm
   ncclComm_t comm;
   int        rank, world;
   int        peer_state;            // 0 not tried yet, 1 windows usable, -1 not available: NCCL moves the data
-  PeerWindow key_window, rle_window;
+  PeerWindow key_window, rle_window, record_window;
   unsigned long long* d_flag;       // scratch of the barrier
   long long* d_status;              // scratch of agree_on_status
+  cudaStream_t ship_stream;         // the planes of the result travel beside the writer chain
+  cudaEvent_t  ship_ready, ship_done;
 };
 
 namespace bwtm
@@ -133,6 +135,64 @@ __global__ void lower_bounds(const KeyT* __restrict__ keys, uint64_t n, const un
     if((unsigned long long)keys[mid] < probe) { lo = mid + 1; } else { hi = mid; }
   }
   out[k] = lo;
+}
+
+// The rank structure of the result without decoding the gathered bytes on every rank: every rank holds the plane
+// chunks of its slice of the merged sequence (K4 wrote them, chunk 0 at the slice's first position) and stores them,
+// shifted onto the global 32-position grid, straight into the record windows of ALL ranks over NVLink. A chunk that
+// two slices share (a slice boundary inside 32 positions) is OR-ed in with atomics; the windows start zeroed.
+constexpr int MAX_SHIP_PEERS = 16;
+constexpr int MAX_SHIP_SLABS = 4;
+
+struct ShipPlan
+{
+  const uint4* slabs[MAX_SHIP_SLABS];   // plane chunks of the slice's slabs
+  uint64_t     slab_chunks;             // chunks per slab (all but the last slab are full)
+  uint64_t     begin, end;              // the slice [begin, end) in merged positions
+  uint4*       peers[MAX_SHIP_PEERS];   // record windows of all ranks (this one included)
+  int          world;
+};
+
+__device__ __forceinline__ uint4 ship_local_chunk(const ShipPlan& plan, int64_t chunk, uint64_t chunks)
+{
+  if(chunk < 0 || (uint64_t)chunk >= chunks) { return make_uint4(0, 0, 0, 0); }
+  return __ldg(plan.slabs[(uint64_t)chunk / plan.slab_chunks] + (uint64_t)chunk % plan.slab_chunks);
+}
+
+__global__ void __launch_bounds__(256)
+ship_planes(ShipPlan plan)
+{
+  const uint64_t first_global = plan.begin >> 5, last_global = (plan.end + 31) >> 5;   // global chunks [first, last)
+  const uint64_t g = first_global + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if(g >= last_global) { return; }
+  const uint64_t chunks = (plan.end - plan.begin + 31) >> 5;
+  // global chunk g starts at slice position 32 g - begin: local chunk `local` at bit `offset`
+  const int64_t start = (int64_t)(g << 5) - (int64_t)plan.begin;
+  const int64_t local = (start >= 0 ? start >> 5 : -1);
+  const uint32_t offset = (uint32_t)(start & 31);
+  uint4 lo = ship_local_chunk(plan, local, chunks), hi = make_uint4(0, 0, 0, 0);
+  if(offset != 0) { hi = ship_local_chunk(plan, local + 1, chunks); }
+  uint4 value;
+  value.x = __funnelshift_r(lo.x, hi.x, offset); value.y = __funnelshift_r(lo.y, hi.y, offset); value.z = __funnelshift_r(lo.z, hi.z, offset);
+  value.w = 0;
+  // positions of the chunk outside the slice belong to the neighbours
+  uint32_t keep = 0xFFFFFFFFu;
+  if((g << 5) < plan.begin) { keep &= ~low_mask((int)(plan.begin - (g << 5))); }
+  if(((g + 1) << 5) > plan.end) { keep &= low_mask((int)(plan.end - (g << 5))); }
+  value.x &= keep; value.y &= keep; value.z &= keep;
+  const bool shared_chunk = (keep != 0xFFFFFFFFu);
+  for(int p = 0; p < plan.world; p++)
+  {
+    uint4* destination = plan.peers[p] + g;
+    if(!shared_chunk) { *destination = value; }
+    else
+    {
+      uint32_t* words = reinterpret_cast<uint32_t*>(destination);
+      if(value.x != 0) { atomicOr(words, value.x); }
+      if(value.y != 0) { atomicOr(words + 1, value.y); }
+      if(value.z != 0) { atomicOr(words + 2, value.z); }
+    }
+  }
 }
 
 // Merges the sorted pieces [offsets[k], offsets[k+1]) of `src` pairwise, ping-ponging between two buffers
@@ -359,6 +419,16 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   BWTM_TRY(agree_on_status(comm, search_and_sort(), stream, "search and local sort"));
   phase.mark("walk + local sort");
 
+  // Record windows for the planes of the result (see ship_planes): reserved and zeroed now, long before anybody
+  // writes into them; the barrier of the key exchange separates the two.
+  const uint64_t result_records = ((n_a + n_b) >> RECORD_SHIFT) + 1;
+  bool ship_records = false;
+  if(G > 1 && G <= MAX_SHIP_PEERS && options->skip_index == 0 && getenv("BWTM_NCCL_EXCHANGE") == nullptr && getenv("BWTM_RLE_INDEX") == nullptr)
+  {
+    BWTM_TRY(window_reserve(comm, &(comm->record_window), result_records * 64, stream, &ship_records));
+    if(ship_records) { BWTM_CUDA(cudaMemsetAsync(comm->record_window.local, 0, result_records * 64, stream)); }
+  }
+
   // 2. splitters: smallest p with p + #{keys < p} >= k (n_a + n_b) / G
   timer.start();
   auto exchange_start = std::chrono::steady_clock::now();
@@ -552,6 +622,35 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   };
   BWTM_TRY(agree_on_status(comm, interleave_slabs(), stream, "merge of the received values and interleave"));
   phase.mark("interleave + runs");
+  // All ranks take the same route to the result's rank structure: planes shipped (every slice was interleaved in
+  // parallel slabs and the key exchange went through the windows, whose barrier ordered the zeroing) or bytes decoded.
+  {
+    unsigned long long can_ship = (ship_records && direct && (parallel || slice == 0) ? 1 : 0), everybody = 0;
+    BWTM_CUDA(cudaMemcpyAsync(comm->d_flag, &can_ship, sizeof(can_ship), cudaMemcpyHostToDevice, stream));
+    BWTM_NCCL(api->AllReduce(comm->d_flag, comm->d_flag, 1, ncclUint64, ncclMin, comm->comm, stream));
+    BWTM_CUDA(cudaMemcpyAsync(&everybody, comm->d_flag, sizeof(everybody), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaMemsetAsync(comm->d_flag, 0, sizeof(unsigned long long), stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    ship_records = (everybody != 0);
+  }
+  bool shipping = false;   // the side stream holds work the main stream has to wait for
+  if(ship_records && slice > 0)
+  {
+    ShipPlan plan; std::memset(&plan, 0, sizeof(plan));
+    for(uint64_t k = 0; k < n_slabs; k++) { plan.slabs[k] = merged[k].as<uint4>(); }
+    plan.slab_chunks = slab / 32; plan.begin = begin; plan.end = end; plan.world = G;
+    for(int p = 0; p < G; p++) { plan.peers[p] = reinterpret_cast<uint4*>(comm->record_window.mapped[p]); }
+    uint64_t global_chunks = ((end + 31) >> 5) - (begin >> 5);
+    // On a side stream: the stores over NVLink run beside the writer chain and the gather of the slices; the main
+    // stream picks the side stream up again before the barrier that ends the gather.
+    cudaStream_t ship_on = (comm->ship_stream != nullptr ? comm->ship_stream : stream);
+    if(ship_on != stream) { BWTM_CUDA(cudaEventRecord(comm->ship_ready, stream)); BWTM_CUDA(cudaStreamWaitEvent(ship_on, comm->ship_ready, 0)); }
+    ship_planes<<<(unsigned)div_up(global_chunks, 256), 256, 0, ship_on>>>(plan);
+    BWTM_LAUNCH_CHECK();
+    if(ship_on != stream) { BWTM_CUDA(cudaEventRecord(comm->ship_done, ship_on)); }
+    shipping = (ship_on != stream);
+  }
+  phase.mark("ship planes");
 
   // 7. the writer state comes from the previous slice and goes to the next one
   if(r > 0)
@@ -610,6 +709,8 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   timings->interleave_seconds = interleave_ms * 1e-3;
   timings->encode_seconds = encode_ms * 1e-3;
   received.release(); received_alt.release();
+  // The plane chunks are freed in the order of the main stream: it must not pass the side stream that still reads them.
+  if(shipping) { BWTM_CUDA(cudaStreamWaitEvent(stream, comm->ship_done, 0)); shipping = false; }
   encoders.clear(); merged.clear();
 
   phase.mark("chained writer");
@@ -642,6 +743,7 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
       int peer = (r + 1 + step) % G;
       BWTM_CUDA(cudaMemcpyAsync(comm->rle_window.mapped[peer] + offset, out.ptr, bytes, cudaMemcpyDeviceToDevice, stream));
     }
+    if(shipping) { BWTM_CUDA(cudaStreamWaitEvent(stream, comm->ship_done, 0)); shipping = false; }   // the barrier covers the planes too
     BWTM_TRY(stream_barrier(comm, stream));
     full.ptr = comm->rle_window.local; full.capacity = comm->rle_window.capacity; full.borrowed = true;
   }
@@ -656,6 +758,11 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
       BWTM_NCCL(api->Broadcast(k == r ? (const void*)out.ptr : (const void*)(full.ptr + offset), full.ptr + offset, bytes, ncclUint8, k, comm->comm, stream));
     }
   }
+  if(ship_records && !direct_gather)   // the NCCL broadcasts do not order the shipped planes: an explicit barrier does
+  {
+    if(shipping) { BWTM_CUDA(cudaStreamWaitEvent(stream, comm->ship_done, 0)); shipping = false; }
+    BWTM_TRY(stream_barrier(comm, stream));
+  }
   BWTM_CUDA(cudaStreamSynchronize(stream));
   device_free(out.ptr);
   timings->exchange_seconds += timer.stop() * 1e-3;
@@ -666,9 +773,21 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   timer.start();
   uint64_t counts[SIGMA];
   for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
-  rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
+  if(ship_records)
+  {
+    // The barrier after the gather of the slices also covered the shipped planes: the window holds the planes of
+    // the whole result. They become the records of the new index (a copy: the window stays with the communicator).
+    DeviceBuffer records;
+    rc = records.allocate(result_records * 64, true);
+    if(rc == BWTM_OK && cudaMemcpyAsync(records.ptr, comm->record_window.local, result_records * 64, cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
+    {
+      rc = cuda_failed(cudaGetLastError(), "copy of the record window", __FILE__, __LINE__);
+    }
+    if(rc == BWTM_OK) { rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, false, stream, result, &records, n_a + n_b); }
+  }
+  else { rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result); }
   if(!full.borrowed) { device_free(full.ptr); }
-  timings->index_seconds = timer.stop() * 1e-3;
+  timings->index_seconds += timer.stop() * 1e-3;
   phase.mark("index");
   return rc;
 }
@@ -725,6 +844,13 @@ int bwtm_comm_create(const uint8_t* id, int rank, int world, bwtm_comm** out)
     set_error("cannot allocate the barrier word"); return BWTM_ERR_MEMORY;
   }
   c->d_status = reinterpret_cast<long long*>(c->d_flag + 1);
+  c->ship_stream = nullptr; c->ship_ready = nullptr; c->ship_done = nullptr;
+  if(cudaStreamCreateWithFlags(&(c->ship_stream), cudaStreamNonBlocking) != cudaSuccess ||
+     cudaEventCreateWithFlags(&(c->ship_ready), cudaEventDisableTiming) != cudaSuccess ||
+     cudaEventCreateWithFlags(&(c->ship_done), cudaEventDisableTiming) != cudaSuccess)
+  {
+    cudaGetLastError(); c->ship_stream = nullptr;   // planes are shipped on the main stream instead
+  }
   *out = c;
   return BWTM_OK;
 }
@@ -735,10 +861,14 @@ int bwtm_comm_destroy(bwtm_comm* comm)
   // Call it on all ranks once the last merge has returned everywhere (like ncclCommDestroy): the windows
   // of this rank go away here.
   cudaDeviceSynchronize();
-  window_close(comm, &(comm->key_window)); window_close(comm, &(comm->rle_window));
+  window_close(comm, &(comm->key_window)); window_close(comm, &(comm->rle_window)); window_close(comm, &(comm->record_window));
   if(comm->key_window.local != nullptr) { cudaFree(comm->key_window.local); }
   if(comm->rle_window.local != nullptr) { cudaFree(comm->rle_window.local); }
+  if(comm->record_window.local != nullptr) { cudaFree(comm->record_window.local); }
   if(comm->d_flag != nullptr) { cudaFree(comm->d_flag); }
+  if(comm->ship_stream != nullptr) { cudaStreamDestroy(comm->ship_stream); }
+  if(comm->ship_ready != nullptr) { cudaEventDestroy(comm->ship_ready); }
+  if(comm->ship_done != nullptr) { cudaEventDestroy(comm->ship_done); }
   cudaGetLastError();
   if(nccl()->ok) { nccl()->CommDestroy(comm->comm); }
   delete comm;

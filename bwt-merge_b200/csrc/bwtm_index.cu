@@ -58,9 +58,15 @@ uint64_t device_total_bytes()
   return totals[device];
 }
 
-// All device memory comes from the device's default stream-ordered pool with an unlimited release
-// threshold: buffers freed by one merge are reused by the next one instead of going back to the driver
-// (cudaMalloc/cudaFree of the multi-GB work buffers cost more than the kernels they serve).
+// Device memory comes from two stream-ordered pools with an unlimited release threshold: buffers freed by one merge
+// are reused by the next one instead of going back to the driver (cudaMalloc/cudaFree of the multi-GB work buffers cost
+// more than the kernels they serve).
+//   * the device's default pool holds the WORK buffers of a merge (keys, scratch, slabs);
+//   * a second pool holds what outlives the call that made it: the buffers of an index (run-length bytes, records,
+//     superblock tables, pair records).
+// With one pool the long-lived result of every merge was carved out of the block that had served the largest work
+// buffer, the next merge found no block of that size any more, and the pool kept remapping memory: steady-state
+// merges of config 5 on two GPUs took 0.5 - 4.8 s instead of 0.3 s (profiles/r02_bench_c5_n2_one_pool.json).
 static int configure_pool()
 {
   static thread_local int configured_device = -1;
@@ -75,12 +81,45 @@ static int configure_pool()
   return BWTM_OK;
 }
 
-int device_alloc(void** ptr, uint64_t n)
+static std::mutex resident_pool_mutex;
+static cudaMemPool_t resident_pools[64] = { nullptr };
+
+static int resident_pool(cudaMemPool_t* pool)
+{
+  int device = 0;
+  BWTM_CUDA(cudaGetDevice(&device));
+  if(device < 0 || device >= 64) { set_error("device ordinal out of range"); return BWTM_ERR_CUDA; }
+  std::lock_guard<std::mutex> lock(resident_pool_mutex);
+  if(resident_pools[device] == nullptr)
+  {
+    cudaMemPoolProps props; std::memset(&props, 0, sizeof(props));
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = device;
+    cudaMemPool_t created;
+    BWTM_CUDA(cudaMemPoolCreate(&created, &props));
+    uint64_t threshold = UINT64_MAX;
+    BWTM_CUDA(cudaMemPoolSetAttribute(created, cudaMemPoolAttrReleaseThreshold, &threshold));
+    resident_pools[device] = created;
+  }
+  *pool = resident_pools[device];
+  return BWTM_OK;
+}
+
+int device_alloc(void** ptr, uint64_t n, bool resident)
 {
   *ptr = nullptr;
   if(n == 0) { n = 16; }
   BWTM_TRY(configure_pool());
-  cudaError_t err = cudaMallocAsync(ptr, n, 0);
+  cudaError_t err;
+  if(resident)
+  {
+    cudaMemPool_t pool;
+    BWTM_TRY(resident_pool(&pool));
+    err = cudaMallocFromPoolAsync(ptr, n, pool, 0);
+  }
+  else { err = cudaMallocAsync(ptr, n, 0); }
   if(err != cudaSuccess)
   {
     *ptr = nullptr;
@@ -96,10 +135,10 @@ void device_free(void* ptr)
   if(ptr != nullptr) { cudaFreeAsync(ptr, 0); }
 }
 
-int DeviceBuffer::allocate(uint64_t n)
+int DeviceBuffer::allocate(uint64_t n, bool resident)
 {
   this->release();
-  BWTM_TRY(device_alloc(&(this->ptr), n));
+  BWTM_TRY(device_alloc(&(this->ptr), n, resident));
   this->bytes = (n == 0 ? 16 : n);
   return BWTM_OK;
 }
@@ -427,7 +466,7 @@ int index_from_planes(uint8_t* d_rle, uint64_t rle_bytes, uint4* d_records, uint
 {
   uint64_t n_records = (size >> RECORD_SHIFT) + 1;
   uint64_t n_super = ((n_records - 1) >> SUPER_RECORD_SHIFT) + 1;
-  DeviceBuffer super; BWTM_TRY(super.allocate(n_super * SUPER_STRIDE * sizeof(uint64_t)));
+  DeviceBuffer super; BWTM_TRY(super.allocate(n_super * SUPER_STRIDE * sizeof(uint64_t), true));
   BWTM_CUDA(cudaMemsetAsync(super.ptr, 0, n_super * SUPER_STRIDE * sizeof(uint64_t), stream));
 
   DeviceBuffer counts; BWTM_TRY(counts.allocate(5 * n_records * sizeof(uint32_t)));
@@ -493,7 +532,7 @@ int index_from_device_rle(uint8_t* d_rle, uint64_t rle_bytes, cudaStream_t strea
   if(size == 0) { set_error("BWT decodes to an empty sequence"); return BWTM_ERR_ARGUMENT; }
 
   uint64_t n_records = (size >> RECORD_SHIFT) + 1;
-  DeviceBuffer records; BWTM_TRY(records.allocate(n_records * 64));
+  DeviceBuffer records; BWTM_TRY(records.allocate(n_records * 64, true));
   BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, n_records * 64, stream));
   k0_fill_planes<<<(unsigned)div_up(blocks, K0_THREADS), K0_THREADS, 0, stream>>>(
     d_rle, rle_bytes, blocks, starts.as<uint64_t>(), records.as<uint32_t>());
@@ -624,7 +663,7 @@ int bwtm_index_create_device(const void* rle_device, uint64_t rle_bytes, bwtm_in
   if(rle_device == nullptr || out == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
   *out = nullptr;
   BWTM_TRY(check_device());
-  DeviceBuffer rle; BWTM_TRY(rle.allocate(rle_bytes + RLE_PADDING));
+  DeviceBuffer rle; BWTM_TRY(rle.allocate(rle_bytes + RLE_PADDING, true));
   BWTM_CUDA(cudaMemcpy(rle.ptr, rle_device, rle_bytes, cudaMemcpyDeviceToDevice));
   BWTM_CUDA(cudaMemset(rle.as<uint8_t>() + rle_bytes, 0, RLE_PADDING));
   BWTM_TRY(index_from_device_rle(rle.as<uint8_t>(), rle_bytes, 0, out));
@@ -637,7 +676,7 @@ int bwtm_index_create(const uint8_t* rle, uint64_t rle_bytes, const uint64_t* ex
   if(rle == nullptr || out == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
   *out = nullptr;
   BWTM_TRY(check_device());
-  DeviceBuffer d_rle; BWTM_TRY(d_rle.allocate(rle_bytes + RLE_PADDING));
+  DeviceBuffer d_rle; BWTM_TRY(d_rle.allocate(rle_bytes + RLE_PADDING, true));
   BWTM_CUDA(cudaMemcpy(d_rle.ptr, rle, rle_bytes, cudaMemcpyHostToDevice));
   BWTM_CUDA(cudaMemset(d_rle.as<uint8_t>() + rle_bytes, 0, RLE_PADDING));
   bwtm_index* index = nullptr;
@@ -682,7 +721,7 @@ int bwtm_index_create_pair(const uint8_t* rle_a, uint64_t rle_bytes_a, const uin
   *out_a = nullptr; *out_b = nullptr;
   BWTM_TRY(check_device());
   DeviceBuffer d_a, d_b;
-  BWTM_TRY(d_a.allocate(rle_bytes_a + RLE_PADDING)); BWTM_TRY(d_b.allocate(rle_bytes_b + RLE_PADDING));
+  BWTM_TRY(d_a.allocate(rle_bytes_a + RLE_PADDING, true)); BWTM_TRY(d_b.allocate(rle_bytes_b + RLE_PADDING, true));
   BWTM_CUDA(cudaMemsetAsync(d_a.as<uint8_t>() + rle_bytes_a, 0, RLE_PADDING, 0));
   BWTM_CUDA(cudaMemsetAsync(d_b.as<uint8_t>() + rle_bytes_b, 0, RLE_PADDING, 0));
   BWTM_CUDA(cudaStreamSynchronize(0));   // the buffers come from stream 0's pool: they are usable on the copy stream from here on
@@ -728,9 +767,15 @@ int bwtm_memory_stats(uint64_t* used_bytes, uint64_t* peak_bytes, int reset_peak
   uint64_t used = 0, peak = 0;
   BWTM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used));
   BWTM_CUDA(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &peak));
-  if(used_bytes != nullptr) { *used_bytes = used; }
-  if(peak_bytes != nullptr) { *peak_bytes = peak; }
   if(reset_peak) { uint64_t zero = 0; BWTM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrUsedMemHigh, &zero)); }
+  cudaMemPool_t resident;
+  BWTM_TRY(resident_pool(&resident));   // the indexes live in a pool of their own: the sum of the two peaks bounds the real one
+  uint64_t resident_used = 0, resident_peak = 0;
+  BWTM_CUDA(cudaMemPoolGetAttribute(resident, cudaMemPoolAttrUsedMemCurrent, &resident_used));
+  BWTM_CUDA(cudaMemPoolGetAttribute(resident, cudaMemPoolAttrUsedMemHigh, &resident_peak));
+  if(reset_peak) { uint64_t zero = 0; BWTM_CUDA(cudaMemPoolSetAttribute(resident, cudaMemPoolAttrUsedMemHigh, &zero)); }
+  if(used_bytes != nullptr) { *used_bytes = used + resident_used; }
+  if(peak_bytes != nullptr) { *peak_bytes = peak + resident_peak; }
   return BWTM_OK;
 }
 

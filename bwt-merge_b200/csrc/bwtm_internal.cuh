@@ -45,7 +45,7 @@ inline DeviceIndex device_view(const bwtm_index* index)
 uint64_t device_total_bytes();   // of the current device, cached
 
 // Stream-ordered pool allocation (bwtm_index.cu).
-int device_alloc(void** ptr, uint64_t bytes);
+int device_alloc(void** ptr, uint64_t bytes, bool resident = false);   // resident: outlives the call (an index's buffers)
 void device_free(void* ptr);
 
 // RAII device buffer on the pool.
@@ -57,7 +57,7 @@ struct DeviceBuffer
   ~DeviceBuffer() { this->release(); }
   DeviceBuffer(const DeviceBuffer&) = delete;
   DeviceBuffer& operator=(const DeviceBuffer&) = delete;
-  int allocate(uint64_t n);                 // BWTM_OK or BWTM_ERR_MEMORY
+  int allocate(uint64_t n, bool resident = false);   // BWTM_OK or BWTM_ERR_MEMORY
   void release();
   void* detach() { void* p = ptr; ptr = nullptr; bytes = 0; return p; }
   template<class T> T* as() const { return static_cast<T*>(ptr); }

@@ -1066,7 +1066,7 @@ int bit_length_host(uint64_t v) { int n = 0; while(v > 0) { n++; v >>= 1; } retu
 int finish_index(OutputBuffer* out, uint64_t rle_bytes, const uint64_t* counts, uint64_t sequences, bool skip_index,
                  cudaStream_t stream, bwtm_index** result, DeviceBuffer* filled_records, uint64_t size)
 {
-  DeviceBuffer exact; BWTM_TRY(exact.allocate(rle_bytes + RLE_PADDING));
+  DeviceBuffer exact; BWTM_TRY(exact.allocate(rle_bytes + RLE_PADDING, true));
   BWTM_CUDA(cudaMemcpyAsync(exact.ptr, out->ptr, rle_bytes, cudaMemcpyDeviceToDevice, stream));
   BWTM_CUDA(cudaMemsetAsync(exact.as<uint8_t>() + rle_bytes, 0, RLE_PADDING, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
@@ -1140,7 +1140,7 @@ int index_from_symbols(const uint8_t* d_symbols, uint64_t n, uint64_t slab_symbo
   if((reinterpret_cast<uintptr_t>(d_symbols) & 15) != 0) { set_error("symbol array is not 16-byte aligned"); return BWTM_ERR_INTERNAL; }
   DeviceBuffer records;
   uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
-  BWTM_TRY(records.allocate(record_bytes));
+  BWTM_TRY(records.allocate(record_bytes, true));
   BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
   BWTM_TRY(planes_from_symbols(d_symbols, 0, n, records.as<uint4>(), stream));
   return index_from_filled_records(records, n, slab_symbols, stream, out);
@@ -1260,7 +1260,7 @@ int index_from_run_bytes(const uint8_t* d_runs, uint64_t n_runs, int layout, uin
   const uint64_t n = tail[0];
   DeviceBuffer records;
   uint64_t record_bytes = ((n >> RECORD_SHIFT) + 1) * 64;
-  BWTM_TRY(records.allocate(record_bytes));
+  BWTM_TRY(records.allocate(record_bytes, true));
   BWTM_CUDA(cudaMemsetAsync(records.ptr, 0, record_bytes, stream));
   run_bytes_fill<<<(unsigned)blocks, 256, 0, stream>>>(d_runs, n_runs, layout, block_start, records.as<uint32_t>());
   BWTM_LAUNCH_CHECK();
@@ -1358,16 +1358,18 @@ static uint64_t available_device_bytes()
     uint64_t reserved = 0, used = 0;
     if(cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
        cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used) { available += reserved - used; }
-  }
+  }   // (what the pool of the indexes holds in reserve is not counted: it serves the result of the merge)
   cudaGetLastError();
   return available;
 }
 
-// Number of search batches: options.sequence_blocks when given (> 0), else 1 unless two full key buffers would take
-// more than half of the memory that is available now (only looked at when they take more than an eighth of the
-// device's memory: small merges never pay for the query).
-static uint64_t choose_batches(const bwtm_merge_options* options, uint64_t sequences, uint64_t n_b, uint64_t key_bytes)
+// Number of search batches: options.sequence_blocks when given (> 0); else 1 whenever the one-shot merge fits in the
+// memory that is available now -- two key buffers, the records of the result, the output bytes and the slab work
+// buffers -- and otherwise as many batches as make the two batch-sized buffers take an eighth of it. The free memory is
+// only asked when the key buffers exceed an eighth of the device (small merges never pay for the query).
+static uint64_t choose_batches(const bwtm_merge_options* options, const bwtm_index* a, const bwtm_index* b, uint64_t key_bytes)
 {
+  const uint64_t n_b = b->size;
   uint64_t batches = options->sequence_blocks;
   if(const char* env = getenv("BWTM_SEQUENCE_BLOCKS")) { batches = strtoull(env, nullptr, 10); }
   if(batches == 0)
@@ -1375,15 +1377,17 @@ static uint64_t choose_batches(const bwtm_merge_options* options, uint64_t seque
     batches = 1;
     if(2 * n_b * key_bytes > device_total_bytes() / 8)
     {
-      uint64_t available = available_device_bytes();
-      if(available > 0 && 2 * n_b * key_bytes > available / 2)
+      const uint64_t available = available_device_bytes();
+      const uint64_t rle_bytes = a->rle_bytes + b->rle_bytes;
+      const uint64_t one_shot = 2 * n_b * key_bytes + (a->size + b->size) / 2 + rle_bytes + (rle_bytes >> 2) + (6ull << 30);
+      if(available > 0 && one_shot > available - (available >> 4))
       {
-        uint64_t batch_budget = std::max<uint64_t>(available / 16, 1ull << 28);   // two batch-sized buffers take an eighth
+        uint64_t batch_budget = std::max<uint64_t>(available / 16, 1ull << 28);
         batches = div_up(n_b * key_bytes, batch_budget);
       }
     }
   }
-  return std::max<uint64_t>(1, std::min(batches, sequences));
+  return std::max<uint64_t>(1, std::min(batches, b->sequences));
 }
 
 template<class KeyT>
@@ -1530,7 +1534,7 @@ static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* op
   cudaStream_t stream = 0;
   uint64_t n_b = b->size;
   BWTM_TRY(prepare_walk(a, b, b->size, stream, timings));
-  const uint64_t batches = choose_batches(options, b->sequences, n_b, sizeof(KeyT));
+  const uint64_t batches = choose_batches(options, a, b, sizeof(KeyT));
   if(batches > 1) { return merge_in_batches<KeyT>(a, b, options, batches, result, timings); }
   timings->search_batches = 1;
   DeviceBuffer keys, alt;
@@ -1603,7 +1607,7 @@ static int merge_impl(bwtm_index* a, bwtm_index* b, const bwtm_merge_options* op
   if(rc == BWTM_OK && options->skip_index == 0 && getenv("BWTM_RLE_INDEX") == nullptr)
   {
     uint64_t record_bytes = (((a->size + b->size) >> RECORD_SHIFT) + 1) * 64;
-    rc = records.allocate(record_bytes);
+    rc = records.allocate(record_bytes, true);
     if(rc == BWTM_OK && cudaMemsetAsync(records.ptr, 0, record_bytes, stream) != cudaSuccess) { set_error("cannot clear the records"); rc = BWTM_ERR_CUDA; }
   }
   if(rc == BWTM_OK)

@@ -289,8 +289,8 @@ int ensure_pair_index(bwtm_index* index, cudaStream_t stream)
   const uint64_t n_pair_records = (index->size >> PAIR_SHIFT) + 1;
   const uint64_t n_pair_super = ((n_pair_records - 1) >> (PAIR_SUPER_SHIFT - PAIR_SHIFT)) + 1;
   DeviceBuffer pairs, super2, totals;
-  BWTM_TRY(pairs.allocate(n_pair_records * PAIR_WORDS * sizeof(uint32_t)));
-  BWTM_TRY(super2.allocate(n_pair_super * PAIR_SUPER_STRIDE * sizeof(uint64_t)));
+  BWTM_TRY(pairs.allocate(n_pair_records * PAIR_WORDS * sizeof(uint32_t), true));
+  BWTM_TRY(super2.allocate(n_pair_super * PAIR_SUPER_STRIDE * sizeof(uint64_t), true));
   BWTM_TRY(totals.allocate(n_pair_super * 25 * sizeof(unsigned long long)));
   const uint64_t n_chunks = 2 * n_pair_records;
   const uint64_t grid_chunks = div_up(n_chunks, 4) * 4;
