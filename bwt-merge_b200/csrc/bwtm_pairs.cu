@@ -342,9 +342,13 @@ int prepare_walk(bwtm_index* a, bwtm_index* b, uint64_t walked_bases, cudaStream
     // that per inserted base. An index that already has them only costs the other side's pass.
     const uint64_t build = (a->d_pairs == nullptr ? a->size : 0) + (b->d_pairs == nullptr ? b->size : 0);
     want = (build <= 4 * walked_bases);
-    // 2 bytes per symbol on top of the basic records: not when that would crowd out the rank array itself.
+    // 2 bytes per symbol on top of the basic records: not when that would crowd out the rank array itself (two key
+    // buffers for the bases this GPU walks) or take more than a third of the device.
     const uint64_t total_bytes = device_total_bytes();
-    if(want && total_bytes > 0 && pair_index_bytes(a->size) + pair_index_bytes(b->size) > total_bytes / 3) { want = false; }
+    const uint64_t pair_bytes = pair_index_bytes(a->size) + pair_index_bytes(b->size);
+    const uint64_t key_bytes = 2 * walked_bases * (a->size < 0xFFFFFFFFull ? 4 : 8);
+    const uint64_t basic_bytes = a->device_bytes + b->device_bytes - a->pair_bytes - b->pair_bytes;
+    if(want && total_bytes > 0 && (pair_bytes > total_bytes / 3 || pair_bytes + key_bytes + 2 * basic_bytes > total_bytes - total_bytes / 8)) { want = false; }
   }
   if(want)
   {
@@ -452,8 +456,10 @@ __device__ __forceinline__ void complement_masks(uint32_t c, uint32_t& n0, uint3
   n0 = (c & 1u) ? 0u : 0xFFFFFFFFu; n1 = (c & 2u) ? 0u : 0xFFFFFFFFu; n2 = (c & 4u) ? 0u : 0xFFFFFFFFu;
 }
 
-template<class KeyT, class PosT>
-__global__ void __launch_bounds__(PW_THREADS, 4)
+// MIN_CTAS resident CTAs per SM bound the registers (5: 51, 6: 42, 7: 36): the kernel waits for DRAM, so more walkers
+// in flight are worth more than registers (4 CTAs: 45.5 ms, 5: 39.9 ms on config 2; BWTM_WALK_CTAS selects 5, 6 or 7).
+template<class KeyT, class PosT, int MIN_CTAS>
+__global__ void __launch_bounds__(PW_THREADS, MIN_CTAS)
 k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
               KeyT* __restrict__ out, uint64_t capacity, PairWalkCounters* counters, unsigned long long* cursor, WalkHistogram histogram)
 {
@@ -653,19 +659,31 @@ k1_walk_pairs(PairView a, PairView b, uint64_t seq_begin, uint64_t seq_end,
   }
 }
 
+template<class KeyT, class PosT, int MIN_CTAS>
+static int launch_pairs_with(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
+                             KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, int sms, cudaStream_t stream,
+                             WalkHistogram histogram)
+{
+  int per_sm = 0;
+  BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_pairs<KeyT, PosT, MIN_CTAS>, PW_THREADS, 0));
+  if(per_sm < 1) { per_sm = 1; }
+  uint64_t sequences = seq_last + 1 - seq_first;
+  uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, PW_THREADS / PW_LANES));
+  k1_walk_pairs<KeyT, PosT, MIN_CTAS><<<(unsigned)blocks, PW_THREADS, 0, stream>>>(
+    pair_view(a), pair_view(b), seq_first, seq_last + 1, d_out, capacity, static_cast<PairWalkCounters*>(counters), cursor, histogram);
+  return BWTM_OK;
+}
+
 template<class KeyT, class PosT>
 static int launch_pairs(const bwtm_index* a, const bwtm_index* b, uint64_t seq_first, uint64_t seq_last,
                         KeyT* d_out, uint64_t capacity, void* counters, unsigned long long* cursor, int sms, cudaStream_t stream,
                         WalkHistogram histogram)
 {
-  int per_sm = 0;
-  BWTM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k1_walk_pairs<KeyT, PosT>, PW_THREADS, 0));
-  if(per_sm < 1) { per_sm = 1; }
-  uint64_t sequences = seq_last + 1 - seq_first;
-  uint64_t blocks = std::min((uint64_t)sms * per_sm, div_up(sequences, PW_THREADS / PW_LANES));
-  k1_walk_pairs<KeyT, PosT><<<(unsigned)blocks, PW_THREADS, 0, stream>>>(
-    pair_view(a), pair_view(b), seq_first, seq_last + 1, d_out, capacity, static_cast<PairWalkCounters*>(counters), cursor, histogram);
-  return BWTM_OK;
+  int ctas = 6;
+  if(const char* env = getenv("BWTM_WALK_CTAS")) { ctas = atoi(env); }
+  if(ctas <= 5) { return launch_pairs_with<KeyT, PosT, 5>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream, histogram); }
+  if(ctas >= 7) { return launch_pairs_with<KeyT, PosT, 7>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream, histogram); }
+  return launch_pairs_with<KeyT, PosT, 6>(a, b, seq_first, seq_last, d_out, capacity, counters, cursor, sms, stream, histogram);
 }
 
 // Enqueues the two-step walk over the sequences [seq_first, seq_last]. Both indexes must have pair records.

@@ -80,11 +80,15 @@ def main():
         if world > 1:
             dist.barrier()
         times.append(time.perf_counter() - t)
-        log("merge %d: %.1f ms  %s" % (step, times[-1] * 1e3, {k: round(v * 1e3, 1) for k, v in M.timings.as_dict().items() if k.endswith("_seconds")}))
+        t = M.timings.as_dict()
+        log("merge %d: %.1f ms  %s  batches %d, walk records of %d bytes" % (
+            step, times[-1] * 1e3, {k: round(v * 1e3, 1) for k, v in t.items() if k.endswith("_seconds")}, t["search_batches"], t["walk_record_bytes"]))
     best = min(times[1:]) if len(times) > 1 else times[0]
     post = M.count(pats)
     ok_counts = bool(np.array_equal(pre, post))
+    stage = {k[:-8]: round(v * 1e3, 1) for k, v in M.timings.as_dict().items() if k.endswith("_seconds")}
     result = {"config": "two-input merge 2x%dx%dbp reads, %d bp genome, %d GPUs" % (args.reads, args.read_len, args.genome, world),
+              "stages_ms_last_merge": stage, "search_batches": int(M.timings.search_batches), "device_memory_peak_bytes": int(bwtm_b200.memory_stats()[1]),
               "inserted_bases": int(n_b), "merged_symbols": int(n_a + n_b), "merged_rle_bytes": int(M.bytes()),
               "merge_ms": best * 1e3, "merged_bases_per_second": n_b / best, "pattern_counts_match": ok_counts,
               "pattern_occurrences": int(post.sum())}
