@@ -8,6 +8,7 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <vector>
 
 #include <cub/cub.cuh>
 
@@ -107,13 +108,34 @@ static int resident_pool(cudaMemPool_t* pool)
   return BWTM_OK;
 }
 
+// Experiment switch BWTM_RESIDENT: "pool" (default) = the second pool, "default" = everything from the default pool,
+// "malloc" = cudaMalloc for the buffers of an index.
+static int resident_mode()
+{
+  static int mode = -1;
+  if(mode < 0)
+  {
+    const char* env = getenv("BWTM_RESIDENT");
+    mode = (env == nullptr ? 0 : (env[0] == 'd' ? 1 : (env[0] == 'm' ? 2 : 0)));
+  }
+  return mode;
+}
+
+static std::mutex plain_allocations_mutex;
+static std::vector<void*> plain_allocations;   // pointers that came from cudaMalloc
+
 int device_alloc(void** ptr, uint64_t n, bool resident)
 {
   *ptr = nullptr;
   if(n == 0) { n = 16; }
   BWTM_TRY(configure_pool());
   cudaError_t err;
-  if(resident)
+  if(resident && resident_mode() == 2)
+  {
+    err = cudaMalloc(ptr, n);
+    if(err == cudaSuccess) { std::lock_guard<std::mutex> lock(plain_allocations_mutex); plain_allocations.push_back(*ptr); }
+  }
+  else if(resident && resident_mode() == 0)
   {
     cudaMemPool_t pool;
     BWTM_TRY(resident_pool(&pool));
@@ -132,7 +154,16 @@ int device_alloc(void** ptr, uint64_t n, bool resident)
 
 void device_free(void* ptr)
 {
-  if(ptr != nullptr) { cudaFreeAsync(ptr, 0); }
+  if(ptr == nullptr) { return; }
+  if(resident_mode() == 2)
+  {
+    std::lock_guard<std::mutex> lock(plain_allocations_mutex);
+    for(size_t k = 0; k < plain_allocations.size(); k++)
+    {
+      if(plain_allocations[k] == ptr) { plain_allocations[k] = plain_allocations.back(); plain_allocations.pop_back(); cudaFree(ptr); return; }
+    }
+  }
+  cudaFreeAsync(ptr, 0);
 }
 
 int DeviceBuffer::allocate(uint64_t n, bool resident)
@@ -749,6 +780,15 @@ int bwtm_index_create_pair(const uint8_t* rle_a, uint64_t rle_bytes_a, const uin
   if(cudaStreamWaitEvent(0, arrived_a, 0) != cudaSuccess) { return failed("cannot order the streams"); }
   rc = index_from_device_rle(d_a.as<uint8_t>(), rle_bytes_a, 0, &index_a);
   if(rc == BWTM_OK) { d_a.detach(); rc = check_counts(index_a, expected_counts_a); }
+  if(rc == BWTM_OK)
+  {
+    // The second input is still on its way: the pair records of the first one (which a merge of the two would build
+    // first thing) are made meanwhile. The second input's length is not known yet: its bytes scale it.
+    uint64_t expected_b = 0;
+    if(expected_counts_b != nullptr) { for(int c = 0; c < SIGMA; c++) { expected_b += expected_counts_b[c]; } }
+    else { expected_b = (uint64_t)((double)index_a->size * ((double)rle_bytes_b / (double)rle_bytes_a)); }
+    build_pairs_ahead(index_a, expected_b, 0);
+  }
   if(rc == BWTM_OK && cudaStreamWaitEvent(0, arrived_b, 0) != cudaSuccess) { set_error("cannot order the streams"); rc = BWTM_ERR_CUDA; }
   if(rc == BWTM_OK) { rc = index_from_device_rle(d_b.as<uint8_t>(), rle_bytes_b, 0, &index_b); }
   if(rc == BWTM_OK) { d_b.detach(); rc = check_counts(index_b, expected_counts_b); }

@@ -75,6 +75,7 @@ int planes_from_symbols(const uint8_t* d_symbols, uint64_t first_position, uint6
 uint64_t pair_index_bytes(uint64_t size);
 int ensure_pair_index(bwtm_index* index, cudaStream_t stream);
 void release_pair_index(bwtm_index* index);
+void build_pairs_ahead(bwtm_index* a, uint64_t expected_b_size, cudaStream_t stream);
 
 // Per-64-byte-block symbol counts and their exclusive scan (block start positions).
 int rle_block_starts(const uint8_t* d_rle, uint64_t rle_bytes, uint64_t* d_starts /* blocks + 1 */, cudaStream_t stream);

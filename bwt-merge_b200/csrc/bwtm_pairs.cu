@@ -289,8 +289,12 @@ int ensure_pair_index(bwtm_index* index, cudaStream_t stream)
   const uint64_t n_pair_records = (index->size >> PAIR_SHIFT) + 1;
   const uint64_t n_pair_super = ((n_pair_records - 1) >> (PAIR_SUPER_SHIFT - PAIR_SHIFT)) + 1;
   DeviceBuffer pairs, super2, totals;
-  BWTM_TRY(pairs.allocate(n_pair_records * PAIR_WORDS * sizeof(uint32_t), true));
-  BWTM_TRY(super2.allocate(n_pair_super * PAIR_SUPER_STRIDE * sizeof(uint64_t), true));
+  // From the default pool, not from the pool of the other index buffers: the walk reads these gigabytes at random
+  // and is sensitive to how they are mapped (config 2: 41.0 ms here, 44.0 ms from the second pool, 39.5 ms from
+  // cudaMalloc, whose cost per index the end-to-end path would not get back; profiles/r02_pool_placement.txt). They are
+  // built before a merge allocates its work buffers, so they do not cut up the blocks those are reused from.
+  BWTM_TRY(pairs.allocate(n_pair_records * PAIR_WORDS * sizeof(uint32_t)));
+  BWTM_TRY(super2.allocate(n_pair_super * PAIR_SUPER_STRIDE * sizeof(uint64_t)));
   BWTM_TRY(totals.allocate(n_pair_super * 25 * sizeof(unsigned long long)));
   const uint64_t n_chunks = 2 * n_pair_records;
   const uint64_t grid_chunks = div_up(n_chunks, 4) * 4;
@@ -332,24 +336,39 @@ bool walk_uses_pairs(const bwtm_index* a, const bwtm_index* b)
   return (a->d_pairs != nullptr && b->d_pairs != nullptr && walk_policy() >= 0);
 }
 
+// The decision of prepare_walk for indexes of n_a and n_b symbols of which `build` symbols still lack pair records,
+// when this GPU walks `walked_bases` of b.
+static bool pairs_pay(uint64_t n_a, uint64_t n_b, uint64_t build, uint64_t walked_bases, uint64_t basic_bytes)
+{
+  const int policy = walk_policy();
+  if(policy != 0) { return (policy > 0); }
+  // Building the records is a streaming pass over an index (a few ps per symbol); the walk saves about four times
+  // that per inserted base. An index that already has them only costs the other side's pass.
+  if(build > 4 * walked_bases) { return false; }
+  // 2 bytes per symbol on top of the basic records: not when that would crowd out the rank array itself (two key
+  // buffers for the bases this GPU walks) or take more than a third of the device.
+  const uint64_t total_bytes = device_total_bytes();
+  const uint64_t pair_bytes = pair_index_bytes(n_a) + pair_index_bytes(n_b);
+  const uint64_t key_bytes = 2 * walked_bases * (n_a < 0xFFFFFFFFull ? 4 : 8);
+  if(total_bytes > 0 && (pair_bytes > total_bytes / 3 || pair_bytes + key_bytes + 2 * basic_bytes > total_bytes - total_bytes / 8)) { return false; }
+  return true;
+}
+
+// For bwtm_index_create_pair: the pair records of the first input, built while the second one is still uploading,
+// when a merge of the two would build them anyway. Failure is not an error (the merge decides again).
+void build_pairs_ahead(bwtm_index* a, uint64_t expected_b_size, cudaStream_t stream)
+{
+  if(a->d_pairs != nullptr || expected_b_size == 0) { return; }
+  const uint64_t basic_bytes = a->device_bytes + (uint64_t)((double)a->device_bytes * ((double)expected_b_size / (double)std::max<uint64_t>(a->size, 1)));
+  if(!pairs_pay(a->size, expected_b_size, a->size + expected_b_size, expected_b_size, basic_bytes)) { return; }
+  if(ensure_pair_index(a, stream) != BWTM_OK) { release_pair_index(a); cudaGetLastError(); }
+}
+
 int prepare_walk(bwtm_index* a, bwtm_index* b, uint64_t walked_bases, cudaStream_t stream, bwtm_timings* timings)
 {
   const int policy = walk_policy();
-  bool want = (policy > 0);
-  if(policy == 0)
-  {
-    // Building the records is a streaming pass over an index (a few ps per symbol); the walk saves about four times
-    // that per inserted base. An index that already has them only costs the other side's pass.
-    const uint64_t build = (a->d_pairs == nullptr ? a->size : 0) + (b->d_pairs == nullptr ? b->size : 0);
-    want = (build <= 4 * walked_bases);
-    // 2 bytes per symbol on top of the basic records: not when that would crowd out the rank array itself (two key
-    // buffers for the bases this GPU walks) or take more than a third of the device.
-    const uint64_t total_bytes = device_total_bytes();
-    const uint64_t pair_bytes = pair_index_bytes(a->size) + pair_index_bytes(b->size);
-    const uint64_t key_bytes = 2 * walked_bases * (a->size < 0xFFFFFFFFull ? 4 : 8);
-    const uint64_t basic_bytes = a->device_bytes + b->device_bytes - a->pair_bytes - b->pair_bytes;
-    if(want && total_bytes > 0 && (pair_bytes > total_bytes / 3 || pair_bytes + key_bytes + 2 * basic_bytes > total_bytes - total_bytes / 8)) { want = false; }
-  }
+  const uint64_t build = (a->d_pairs == nullptr ? a->size : 0) + (b->d_pairs == nullptr ? b->size : 0);
+  bool want = pairs_pay(a->size, b->size, build, walked_bases, a->device_bytes + b->device_bytes - a->pair_bytes - b->pair_bytes);
   if(want)
   {
     EventTimer timer(stream);
