@@ -123,6 +123,26 @@ static int resident_mode()
 
 static std::mutex plain_allocations_mutex;
 static std::vector<void*> plain_allocations;   // pointers that came from cudaMalloc
+static std::vector<uint64_t> plain_sizes;
+static uint64_t plain_bytes = 0;
+
+// cudaMalloc instead of a pool: for the few large structures that are read at random for a long time (pair records
+// built ahead of time), where the plain allocation's mapping is measurably faster and its cost is paid once.
+int device_alloc_plain(void** ptr, uint64_t n)
+{
+  *ptr = nullptr;
+  if(n == 0) { n = 16; }
+  cudaError_t err = cudaMalloc(ptr, n);
+  if(err != cudaSuccess)
+  {
+    *ptr = nullptr; cudaGetLastError();
+    set_error("device allocation of %llu bytes failed: %s", (unsigned long long)n, cudaGetErrorString(err));
+    return BWTM_ERR_MEMORY;
+  }
+  std::lock_guard<std::mutex> lock(plain_allocations_mutex);
+  plain_allocations.push_back(*ptr); plain_sizes.push_back(n); plain_bytes += n;
+  return BWTM_OK;
+}
 
 int device_alloc(void** ptr, uint64_t n, bool resident)
 {
@@ -130,12 +150,8 @@ int device_alloc(void** ptr, uint64_t n, bool resident)
   if(n == 0) { n = 16; }
   BWTM_TRY(configure_pool());
   cudaError_t err;
-  if(resident && resident_mode() == 2)
-  {
-    err = cudaMalloc(ptr, n);
-    if(err == cudaSuccess) { std::lock_guard<std::mutex> lock(plain_allocations_mutex); plain_allocations.push_back(*ptr); }
-  }
-  else if(resident && resident_mode() == 0)
+  if(resident && resident_mode() == 2) { return device_alloc_plain(ptr, n); }
+  if(resident && resident_mode() == 0)
   {
     cudaMemPool_t pool;
     BWTM_TRY(resident_pool(&pool));
@@ -155,12 +171,18 @@ int device_alloc(void** ptr, uint64_t n, bool resident)
 void device_free(void* ptr)
 {
   if(ptr == nullptr) { return; }
-  if(resident_mode() == 2)
   {
     std::lock_guard<std::mutex> lock(plain_allocations_mutex);
     for(size_t k = 0; k < plain_allocations.size(); k++)
     {
-      if(plain_allocations[k] == ptr) { plain_allocations[k] = plain_allocations.back(); plain_allocations.pop_back(); cudaFree(ptr); return; }
+      if(plain_allocations[k] == ptr)
+      {
+        plain_bytes -= plain_sizes[k];
+        plain_allocations[k] = plain_allocations.back(); plain_allocations.pop_back();
+        plain_sizes[k] = plain_sizes.back(); plain_sizes.pop_back();
+        cudaFree(ptr);
+        return;
+      }
     }
   }
   cudaFreeAsync(ptr, 0);
@@ -814,8 +836,10 @@ int bwtm_memory_stats(uint64_t* used_bytes, uint64_t* peak_bytes, int reset_peak
   BWTM_CUDA(cudaMemPoolGetAttribute(resident, cudaMemPoolAttrUsedMemCurrent, &resident_used));
   BWTM_CUDA(cudaMemPoolGetAttribute(resident, cudaMemPoolAttrUsedMemHigh, &resident_peak));
   if(reset_peak) { uint64_t zero = 0; BWTM_CUDA(cudaMemPoolSetAttribute(resident, cudaMemPoolAttrUsedMemHigh, &zero)); }
-  if(used_bytes != nullptr) { *used_bytes = used + resident_used; }
-  if(peak_bytes != nullptr) { *peak_bytes = peak + resident_peak; }
+  uint64_t plain = 0;
+  { std::lock_guard<std::mutex> lock(plain_allocations_mutex); plain = plain_bytes; }   // pair records built ahead of time
+  if(used_bytes != nullptr) { *used_bytes = used + resident_used + plain; }
+  if(peak_bytes != nullptr) { *peak_bytes = peak + resident_peak + plain; }
   return BWTM_OK;
 }
 

@@ -46,6 +46,7 @@ uint64_t device_total_bytes();   // of the current device, cached
 
 // Stream-ordered pool allocation (bwtm_index.cu).
 int device_alloc(void** ptr, uint64_t bytes, bool resident = false);   // resident: outlives the call (an index's buffers)
+int device_alloc_plain(void** ptr, uint64_t bytes);                     // cudaMalloc; freed by device_free as well
 void device_free(void* ptr);
 
 // RAII device buffer on the pool.
@@ -73,7 +74,7 @@ int planes_from_symbols(const uint8_t* d_symbols, uint64_t first_position, uint6
 
 // Pair records (bwtm_pairs.cu): two backward steps per record read.
 uint64_t pair_index_bytes(uint64_t size);
-int ensure_pair_index(bwtm_index* index, cudaStream_t stream);
+int ensure_pair_index(bwtm_index* index, cudaStream_t stream, bool built_ahead = false);   // built_ahead: plain allocation
 void release_pair_index(bwtm_index* index);
 void build_pairs_ahead(bwtm_index* a, uint64_t expected_b_size, cudaStream_t stream);
 

@@ -282,7 +282,7 @@ uint64_t pair_index_bytes(uint64_t size)
 }
 
 // Builds the pair records of `index` (kept with the index until it is destroyed). No-op when they exist.
-int ensure_pair_index(bwtm_index* index, cudaStream_t stream)
+int ensure_pair_index(bwtm_index* index, cudaStream_t stream, bool built_ahead)
 {
   if(index->d_pairs != nullptr) { return BWTM_OK; }
   if(index->d_records == nullptr) { set_error("the index has no rank structure"); return BWTM_ERR_ARGUMENT; }
@@ -293,7 +293,9 @@ int ensure_pair_index(bwtm_index* index, cudaStream_t stream)
   // and is sensitive to how they are mapped (config 2: 41.0 ms here, 44.0 ms from the second pool, 39.5 ms from
   // cudaMalloc, whose cost per index the end-to-end path would not get back; profiles/r02_pool_placement.txt). They are
   // built before a merge allocates its work buffers, so they do not cut up the blocks those are reused from.
-  BWTM_TRY(pairs.allocate(n_pair_records * PAIR_WORDS * sizeof(uint32_t)));
+  // bwtm_index_build_pairs (built_ahead) takes the plain allocation: it is paid once, outside any merge.
+  if(built_ahead) { BWTM_TRY(device_alloc_plain(&pairs.ptr, n_pair_records * PAIR_WORDS * sizeof(uint32_t))); pairs.bytes = n_pair_records * PAIR_WORDS * sizeof(uint32_t); }
+  else { BWTM_TRY(pairs.allocate(n_pair_records * PAIR_WORDS * sizeof(uint32_t))); }
   BWTM_TRY(super2.allocate(n_pair_super * PAIR_SUPER_STRIDE * sizeof(uint64_t)));
   BWTM_TRY(totals.allocate(n_pair_super * 25 * sizeof(unsigned long long)));
   const uint64_t n_chunks = 2 * n_pair_records;
@@ -747,7 +749,7 @@ extern "C"
 int bwtm_index_build_pairs(bwtm_index* index)
 {
   if(index == nullptr) { set_error("null argument"); return BWTM_ERR_ARGUMENT; }
-  BWTM_TRY(ensure_pair_index(index, 0));
+  BWTM_TRY(ensure_pair_index(index, 0, true));
   BWTM_CUDA(cudaStreamSynchronize(0));
   return BWTM_OK;
 }
