@@ -34,6 +34,7 @@
 #include <cub/cub.cuh>
 
 #include "bwtm_merge.cuh"
+#include "bwtm_batches.cuh"
 
 using namespace bwtm;
 
@@ -792,6 +793,339 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   return rc;
 }
 
+
+//------------------------------------------------------------------------------
+// The distributed merge with the search in batches (options.sequence_blocks > 1): every rank keeps its rank-array
+// values as S sorted runs (bwtm_batches.cuh), the exchange moves the pieces of every run straight into the owners'
+// windows (G S sorted pieces per rank), and the owner merges them range by range while it interleaves, inside the
+// writer chain. Work memory per rank: its values once (+ one batch-sized scratch), then the window; no second copy.
+
+// counts[p] = #{keys < probes[p]} over all runs; per_run[p * S + k] (optional) = the part of run k.
+template<class KeyT>
+__global__ void lower_bounds_runs(const KeyT* __restrict__ keys, const unsigned long long* __restrict__ run_offsets, int S,
+                                  const unsigned long long* __restrict__ probes, int n_probes,
+                                  unsigned long long* __restrict__ counts, unsigned long long* __restrict__ per_run)
+{
+  int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if(p >= n_probes) { return; }
+  unsigned long long probe = probes[p], total = 0;
+  for(int k = 0; k < S; k++)
+  {
+    unsigned long long lo = run_offsets[k], hi = run_offsets[k + 1];
+    while(lo < hi)
+    {
+      unsigned long long mid = lo + (hi - lo) / 2;
+      if((unsigned long long)keys[mid] < probe) { lo = mid + 1; } else { hi = mid; }
+    }
+    if(per_run != nullptr) { per_run[(size_t)p * S + k] = lo - run_offsets[k]; }
+    total += lo - run_offsets[k];
+  }
+  counts[p] = total;
+}
+
+// Steps 8 and 9 of the distributed merge for a slice that sits in `out`: every rank gets all slices (peer windows
+// or NCCL broadcasts) and builds its replica of the rank structure from the bytes.
+static int gather_slices_and_index(bwtm_comm* comm, const bwtm_index* a, const bwtm_index* b, const bwtm_merge_options* options,
+                                   OutputBuffer& out, const EncodeControl& ctl, cudaStream_t stream, bwtm_index** result, bwtm_timings* timings)
+{
+  NcclApi* api = nccl();
+  const int G = comm->world, r = comm->rank;
+  EventTimer timer(stream);
+  timer.start();
+  unsigned long long mine[3] = { out.origin, ctl.out_size - out.origin, ctl.runs_total };
+  std::vector<unsigned long long> slices((size_t)3 * G, 0);
+  DeviceBuffer d_mine, d_slices;
+  BWTM_TRY(d_mine.allocate(sizeof(mine))); BWTM_TRY(d_slices.allocate(slices.size() * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemcpyAsync(d_mine.ptr, mine, sizeof(mine), cudaMemcpyHostToDevice, stream));
+  BWTM_NCCL(api->AllGather(d_mine.ptr, d_slices.ptr, 3, ncclUint64, comm->comm, stream));
+  BWTM_CUDA(cudaMemcpyAsync(slices.data(), d_slices.ptr, slices.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  uint64_t total_bytes = slices[(size_t)3 * (G - 1)] + slices[(size_t)3 * (G - 1) + 1];
+  timings->merged_bytes = total_bytes; timings->merged_runs = slices[(size_t)3 * (G - 1) + 2];
+  for(int k = 0; k < G; k++)
+  {
+    if(slices[(size_t)3 * k] + slices[(size_t)3 * k + 1] > total_bytes) { set_error("inconsistent slice layout"); return BWTM_ERR_INTERNAL; }
+  }
+  OutputBuffer full = { nullptr, 0, 0, nullptr };
+  bool direct_gather = false;
+  BWTM_TRY(window_reserve(comm, &(comm->rle_window), total_bytes + RLE_PADDING, stream, &direct_gather));
+  int rc = BWTM_OK;
+  if(direct_gather)
+  {
+    uint64_t offset = slices[(size_t)3 * r], bytes = slices[(size_t)3 * r + 1];
+    for(int step = 0; bytes > 0 && step < G; step++)
+    {
+      int peer = (r + 1 + step) % G;
+      BWTM_CUDA(cudaMemcpyAsync(comm->rle_window.mapped[peer] + offset, out.ptr, bytes, cudaMemcpyDeviceToDevice, stream));
+    }
+    BWTM_TRY(stream_barrier(comm, stream));
+    full.ptr = comm->rle_window.local; full.capacity = comm->rle_window.capacity; full.borrowed = true;
+  }
+  else
+  {
+    rc = agree_on_status(comm, ensure_capacity(&full, total_bytes + RLE_PADDING, 0, stream), stream, "gather buffer");
+    if(rc != BWTM_OK) { device_free(full.ptr); return rc; }
+    for(int k = 0; k < G; k++)
+    {
+      uint64_t offset = slices[(size_t)3 * k], bytes = slices[(size_t)3 * k + 1];
+      if(bytes == 0) { continue; }
+      BWTM_NCCL(api->Broadcast(k == r ? (const void*)out.ptr : (const void*)(full.ptr + offset), full.ptr + offset, bytes, ncclUint8, k, comm->comm, stream));
+    }
+  }
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  timings->exchange_seconds += timer.stop() * 1e-3;
+  timer.start();
+  uint64_t counts[SIGMA];
+  for(int c = 0; c < SIGMA; c++) { counts[c] = a->counts[c] + b->counts[c]; }
+  rc = finish_index(&full, total_bytes, counts, a->sequences + b->sequences, options->skip_index != 0, stream, result);
+  if(!full.borrowed) { device_free(full.ptr); }
+  timings->index_seconds += timer.stop() * 1e-3;
+  return rc;
+}
+
+template<class KeyT>
+static int merge_distributed_batched(bwtm_comm* comm, bwtm_index* a, bwtm_index* b, const bwtm_merge_options* options, int S,
+                                     bwtm_index** result, bwtm_timings* timings)
+{
+  NcclApi* api = nccl();
+  cudaStream_t stream = 0;
+  const int G = comm->world, r = comm->rank;
+  const uint64_t n_a = a->size, n_b = b->size, m_b = b->sequences;
+  const int bits = bit_length_host(n_a);
+  EventTimer timer(stream);
+  PhaseClock phase(r);
+
+  // 1. search + sort in batches: S sorted runs
+  uint64_t seq_first = 0, seq_count = 0;
+  bwtm_shard_range(m_b, (uint32_t)r, (uint32_t)G, &seq_first, &seq_count);
+  uint64_t capacity = std::min<uint64_t>(n_b, (uint64_t)((double)n_b * ((double)seq_count / (double)m_b) * 1.05) + (1ull << 20));
+  DeviceBuffer runs, scratch;
+  std::vector<unsigned long long> run_offsets(S + 1, 0);
+  auto search_in_batches = [&]() -> int
+  {
+    BWTM_TRY(injected_failure("search", r));
+    BWTM_TRY(prepare_walk(a, b, (uint64_t)((double)n_b * ((double)seq_count / (double)m_b)), stream, timings));
+    float search_ms = 0.0f, sort_ms = 0.0f;
+    for(int attempt = 0; attempt < 2; attempt++)
+    {
+      BWTM_TRY(runs.allocate(std::max<uint64_t>(capacity, 1) * sizeof(KeyT)));
+      bool fits = true;
+      std::fill(run_offsets.begin(), run_offsets.end(), 0);
+      for(int k = 0; k < S && fits; k++)
+      {
+        uint64_t first = seq_first + (uint64_t)(((__uint128_t)seq_count * k) / S), last = seq_first + (uint64_t)(((__uint128_t)seq_count * (k + 1)) / S);
+        run_offsets[k + 1] = run_offsets[k];
+        if(last == first) { continue; }
+        uint64_t emitted = 0;
+        timer.start();
+        int rc = walk_sequences<KeyT>(a, b, first, last - 1, runs.as<KeyT>() + run_offsets[k], capacity - run_offsets[k], &emitted, stream);
+        search_ms += timer.stop();
+        if(rc == BWTM_ERR_CAPACITY) { fits = false; break; }
+        BWTM_TRY(rc);
+        run_offsets[k + 1] = run_offsets[k] + emitted;
+        if(emitted == 0) { continue; }
+        timer.start();
+        if(emitted * sizeof(KeyT) > scratch.bytes) { BWTM_TRY(scratch.allocate(emitted * sizeof(KeyT) + (emitted * sizeof(KeyT) >> 3))); }
+        KeyT* sorted = nullptr;
+        BWTM_TRY(sort_keys<KeyT>(runs.as<KeyT>() + run_offsets[k], scratch.as<KeyT>(), emitted, bits, &sorted, stream, n_a + 1));
+        if(sorted != runs.as<KeyT>() + run_offsets[k])
+        {
+          BWTM_CUDA(cudaMemcpyAsync(runs.as<KeyT>() + run_offsets[k], sorted, emitted * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream));
+        }
+        sort_ms += timer.stop();
+      }
+      if(fits) { break; }
+      for(int k = S; k > 0; k--) { run_offsets[k] = run_offsets[0]; }
+      if(attempt == 1 || capacity == n_b) { set_error("rank array buffer too small"); return BWTM_ERR_CAPACITY; }
+      capacity = n_b;   // sequences of very different lengths: take the upper bound
+    }
+    scratch.release();
+    timings->search_seconds = search_ms * 1e-3; timings->sort_seconds = sort_ms * 1e-3;
+    timings->walk_kernel_launches = S; timings->search_batches = S;
+    return BWTM_OK;
+  };
+  BWTM_TRY(agree_on_status(comm, search_in_batches(), stream, "search and local sort"));
+  const uint64_t local_n = run_offsets[S];
+  DeviceBuffer d_run_offsets;
+  BWTM_TRY(d_run_offsets.allocate((S + 1) * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemcpyAsync(d_run_offsets.ptr, run_offsets.data(), (S + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  phase.mark("walk + local sort");
+
+  // 2. splitters: smallest p with p + #{keys < p} >= k (n_a + n_b) / G
+  timer.start();
+  const int P = G - 1;
+  std::vector<unsigned long long> lo(std::max(P, 1), 0), hi(std::max(P, 1), n_a + 1), target(std::max(P, 1), 0);
+  for(int k = 0; k < P; k++) { target[k] = (unsigned long long)(((__uint128_t)(n_a + n_b) * (k + 1)) / G); }
+  const int PROBES = 31;
+  std::vector<unsigned long long> candidates((size_t)std::max(P, 1) * PROBES, 0), counted((size_t)std::max(P, 1) * PROBES, 0);
+  DeviceBuffer d_probes, d_counts, d_per_run;
+  BWTM_TRY(d_probes.allocate(candidates.size() * sizeof(unsigned long long)));
+  BWTM_TRY(d_counts.allocate(candidates.size() * sizeof(unsigned long long)));
+  BWTM_TRY(d_per_run.allocate((size_t)std::max(P, 1) * S * sizeof(unsigned long long)));
+  for(int iteration = 0; P > 0 && iteration < 66; iteration++)
+  {
+    bool open = false;
+    for(int k = 0; k < P; k++)
+    {
+      open = open || (lo[k] < hi[k]);
+      unsigned long long width = hi[k] - lo[k];
+      for(int t = 0; t < PROBES; t++)
+      {
+        candidates[(size_t)k * PROBES + t] = lo[k] + (unsigned long long)(((__uint128_t)width * (t + 1)) / (PROBES + 1));
+        if(width > 0 && candidates[(size_t)k * PROBES + t] >= hi[k]) { candidates[(size_t)k * PROBES + t] = hi[k] - 1; }
+      }
+    }
+    if(!open) { break; }
+    const int n_probes = P * PROBES;
+    BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, candidates.data(), n_probes * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    lower_bounds_runs<KeyT><<<div_up(n_probes, 128), 128, 0, stream>>>(runs.as<KeyT>(), d_run_offsets.as<unsigned long long>(), S, d_probes.as<unsigned long long>(),
+                                                                        n_probes, d_counts.as<unsigned long long>(), nullptr);
+    BWTM_LAUNCH_CHECK();
+    BWTM_NCCL(api->AllReduce(d_counts.ptr, d_counts.ptr, n_probes, ncclUint64, ncclSum, comm->comm, stream));
+    BWTM_CUDA(cudaMemcpyAsync(counted.data(), d_counts.ptr, n_probes * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+    for(int k = 0; k < P; k++)
+    {
+      if(lo[k] >= hi[k]) { continue; }
+      for(int t = 0; t < PROBES; t++)
+      {
+        unsigned long long c = candidates[(size_t)k * PROBES + t];
+        if(c < lo[k]) { continue; }
+        if(c + counted[(size_t)k * PROBES + t] >= target[k]) { hi[k] = c; break; }
+        lo[k] = c + 1;
+      }
+    }
+  }
+  std::vector<unsigned long long> splitter(G + 1, 0);
+  for(int k = 0; k < P; k++) { splitter[k + 1] = std::max(lo[k], splitter[k]); }
+  splitter[G] = n_a + 1;
+  phase.mark("splitter search");
+
+  // 3. the pieces: bound[d][k] = #{keys of run k below splitter[d]}
+  std::vector<unsigned long long> bound((size_t)(G + 1) * S, 0);
+  if(P > 0)
+  {
+    BWTM_CUDA(cudaMemcpyAsync(d_probes.ptr, splitter.data() + 1, P * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+    lower_bounds_runs<KeyT><<<(unsigned)div_up(P, 32), 32, 0, stream>>>(runs.as<KeyT>(), d_run_offsets.as<unsigned long long>(), S, d_probes.as<unsigned long long>(),
+                                                                        P, d_counts.as<unsigned long long>(), d_per_run.as<unsigned long long>());
+    BWTM_LAUNCH_CHECK();
+    BWTM_CUDA(cudaMemcpyAsync(bound.data() + S, d_per_run.ptr, (size_t)P * S * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+    BWTM_CUDA(cudaStreamSynchronize(stream));
+  }
+  for(int k = 0; k < S; k++) { bound[(size_t)G * S + k] = run_offsets[k + 1] - run_offsets[k]; }
+  // piece[src][dst][k], all-gathered
+  std::vector<unsigned long long> my_pieces((size_t)G * S, 0), pieces((size_t)G * G * S, 0);
+  for(int d = 0; d < G; d++) { for(int k = 0; k < S; k++) { my_pieces[(size_t)d * S + k] = bound[(size_t)(d + 1) * S + k] - bound[(size_t)d * S + k]; } }
+  DeviceBuffer d_my_pieces, d_pieces;
+  BWTM_TRY(d_my_pieces.allocate(my_pieces.size() * sizeof(unsigned long long)));
+  BWTM_TRY(d_pieces.allocate(pieces.size() * sizeof(unsigned long long)));
+  BWTM_CUDA(cudaMemcpyAsync(d_my_pieces.ptr, my_pieces.data(), my_pieces.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+  BWTM_NCCL(api->AllGather(d_my_pieces.ptr, d_pieces.ptr, my_pieces.size(), ncclUint64, comm->comm, stream));
+  BWTM_CUDA(cudaMemcpyAsync(pieces.data(), d_pieces.ptr, pieces.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  auto piece = [&](int src, int dst, int k) -> unsigned long long { return pieces[((size_t)src * G + dst) * S + k]; };
+  uint64_t all_values = 0, b_lo = 0, largest = 0;
+  std::vector<uint64_t> into(G, 0);   // values every rank receives
+  for(int src = 0; src < G; src++) { for(int dst = 0; dst < G; dst++) { for(int k = 0; k < S; k++)
+  {
+    all_values += piece(src, dst, k); into[dst] += piece(src, dst, k);
+    if(dst < r) { b_lo += piece(src, dst, k); }
+  } } }
+  for(int dst = 0; dst < G; dst++) { largest = std::max(largest, into[dst]); }
+  if(all_values != n_b)
+  {
+    set_error("the rank array has %llu values but the inserted BWT has %llu symbols: not a valid multi-string BWT",
+              (unsigned long long)all_values, (unsigned long long)n_b);
+    return BWTM_ERR_INTERNAL;
+  }
+  timings->ra_values = all_values;
+  const uint64_t recv_total = into[r];
+  phase.mark("count matrix");
+
+  // 4. every piece goes straight to its place in the owner's window: ordered by (source rank, run)
+  bool direct = false;
+  BWTM_TRY(window_reserve(comm, &(comm->key_window), std::max<uint64_t>(largest, 1) * sizeof(KeyT), stream, &direct));
+  {
+    int rc = (direct ? BWTM_OK : BWTM_ERR_COMM);
+    if(!direct) { set_error("the batched distributed merge needs peer windows (CUDA IPC between the GPUs)"); }
+    BWTM_TRY(agree_on_status(comm, rc, stream, "peer windows"));
+  }
+  for(int step = 0; step < G; step++)
+  {
+    int peer = (r + step) % G;
+    uint64_t offset = 0;
+    for(int src = 0; src < r; src++) { for(int k = 0; k < S; k++) { offset += piece(src, peer, k); } }
+    for(int k = 0; k < S; k++)
+    {
+      uint64_t count = piece(r, peer, k);
+      if(count > 0)
+      {
+        BWTM_CUDA(cudaMemcpyAsync(reinterpret_cast<KeyT*>(comm->key_window.mapped[peer]) + offset, runs.as<KeyT>() + run_offsets[k] + bound[(size_t)peer * S + k],
+                                  count * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream));
+      }
+      offset += count;
+    }
+  }
+  BWTM_TRY(stream_barrier(comm, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  runs.release();
+  const KeyT* arrived = reinterpret_cast<const KeyT*>(comm->key_window.local);
+  std::vector<unsigned long long> arrived_offsets(1, 0);   // G S sorted runs
+  for(int src = 0; src < G; src++) { for(int k = 0; k < S; k++) { arrived_offsets.push_back(arrived_offsets.back() + piece(src, r, k)); } }
+  timings->exchange_seconds = timer.stop() * 1e-3;
+  phase.mark("all-to-all");
+
+  // 5. + 6. my slice of the merged BWT, merged range by range inside the writer chain
+  const uint64_t a_lo = std::min<uint64_t>(splitter[r], n_a), a_hi = std::min<uint64_t>(splitter[r + 1], n_a);
+  const uint64_t begin = a_lo + b_lo, end = a_hi + b_lo + recv_total;
+  DeviceBuffer control;
+  BWTM_TRY(agree_on_status(comm, control.allocate(sizeof(EncodeControl)), stream, "writer state"));
+  if(r > 0) { BWTM_NCCL(api->Recv(control.ptr, sizeof(EncodeControl), ncclUint8, r - 1, comm->comm, stream)); }
+  else { BWTM_CUDA(cudaMemsetAsync(control.ptr, 0, sizeof(EncodeControl), stream)); }
+  EncodeControl ctl;
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  const unsigned long long POISONED_STATE = ~0ull;
+  const bool upstream_failed = (ctl.out_size == POISONED_STATE);
+  OutputBuffer out = { nullptr, 0, (upstream_failed ? 0 : ctl.out_size), nullptr };
+  const uint64_t estimate = (a->rle_bytes + b->rle_bytes) / G;
+  int rc = BWTM_OK;
+  float merge_ms = 0.0f, interleave_ms = 0.0f, encode_ms = 0.0f;
+  if(upstream_failed) { set_error("an earlier rank of the writer chain failed"); rc = BWTM_ERR_COMM; }
+  else { rc = ensure_capacity(&out, out.origin + estimate + (estimate >> 2) + (1 << 20), out.origin, stream); }
+  if(rc == BWTM_OK) { rc = injected_failure("writer", r); }
+  if(rc == BWTM_OK && end > begin)
+  {
+    rc = merge_ranges<KeyT>(a, b, arrived, arrived_offsets, splitter[r], splitter[r + 1], b_lo, begin, end, options, &out, control.as<EncodeControl>(), false,
+                            &merge_ms, &interleave_ms, &encode_ms, nullptr, stream);
+  }
+  if(rc != BWTM_OK && !upstream_failed)
+  {
+    EncodeControl poisoned; std::memset(&poisoned, 0, sizeof(poisoned)); poisoned.out_size = POISONED_STATE;
+    cudaMemcpyAsync(control.ptr, &poisoned, sizeof(poisoned), cudaMemcpyHostToDevice, stream);
+    cudaStreamSynchronize(stream);
+  }
+  if(r < G - 1) { BWTM_NCCL(api->Send(control.ptr, sizeof(EncodeControl), ncclUint8, r + 1, comm->comm, stream)); }
+  if(rc == BWTM_OK && r == G - 1)
+  {
+    SlabEncoder last; rc = last.init(4096, stream);
+    if(rc == BWTM_OK) { rc = last.finish(&out, control.as<EncodeControl>(), stream); }
+  }
+  rc = agree_on_status(comm, rc, stream, "chained writer");
+  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
+  BWTM_CUDA(cudaStreamSynchronize(stream));
+  timings->exchange_seconds += merge_ms * 1e-3;
+  timings->interleave_seconds = interleave_ms * 1e-3; timings->encode_seconds = encode_ms * 1e-3;
+  phase.mark("chained merge + writer");
+
+  // 7. + 8. the complete result on every rank
+  rc = gather_slices_and_index(comm, a, b, options, out, ctl, stream, result, timings);
+  device_free(out.ptr);
+  phase.mark("gather + index");
+  return rc;
+}
+
 } // namespace bwtm
 
 extern "C"
@@ -892,7 +1226,17 @@ int bwtm_merge_distributed(bwtm_comm* comm, bwtm_index* a, bwtm_index* b, const 
     *out = nullptr;
     uint64_t launches_before = bwtm_kernel_launches();
     auto start = std::chrono::steady_clock::now();
-    if(a->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr) { rc = merge_distributed_impl<uint32_t>(comm, a, b, options, out, &local); }
+    // options.sequence_blocks > 1 (the same on every rank): the search in batches and the range-wise merge.
+    uint64_t batches = options->sequence_blocks;
+    if(const char* env = getenv("BWTM_SEQUENCE_BLOCKS")) { batches = strtoull(env, nullptr, 10); }
+    batches = std::min<uint64_t>(batches, 64);
+    const bool narrow = (a->size < 0xFFFFFFFFull && getenv("BWTM_FORCE_WIDE") == nullptr);
+    if(batches > 1 && comm->world > 1)
+    {
+      rc = (narrow ? merge_distributed_batched<uint32_t>(comm, a, b, options, (int)batches, out, &local)
+                   : merge_distributed_batched<uint64_t>(comm, a, b, options, (int)batches, out, &local));
+    }
+    else if(narrow) { rc = merge_distributed_impl<uint32_t>(comm, a, b, options, out, &local); }
     else { rc = merge_distributed_impl<uint64_t>(comm, a, b, options, out, &local); }
     cudaDeviceSynchronize();
     local.total_seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();

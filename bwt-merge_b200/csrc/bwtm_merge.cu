@@ -21,6 +21,7 @@
 #include <cub/cub.cuh>
 
 #include "bwtm_merge.cuh"
+#include "bwtm_batches.cuh"
 
 namespace bwtm
 {
@@ -1278,73 +1279,6 @@ int index_from_run_bytes(const uint8_t* d_runs, uint64_t n_runs, int layout, uin
 // positions: the pieces of the S runs that fall into a range are gathered, merged pairwise and consumed at once.
 // Peak memory: |b| keys + 2 batch-sized buffers instead of 2 |b| keys.
 
-// splitters[r] = smallest x with x + #{keys < x} >= r * step (r = 0: 0, r = ranges: n_a + 1);
-// bounds[r * S + k] = #{keys of run k below splitters[r]}.
-template<class KeyT>
-__global__ void batch_splitters(const KeyT* __restrict__ keys, const unsigned long long* __restrict__ run_offsets, int S,
-                                unsigned long long n_a, unsigned long long step, unsigned long long ranges,
-                                unsigned long long* __restrict__ splitters, unsigned long long* __restrict__ bounds)
-{
-  unsigned long long r = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if(r > ranges) { return; }
-  auto below = [&](unsigned long long x, int k) -> unsigned long long
-  {
-    unsigned long long lo = run_offsets[k], hi = run_offsets[k + 1];
-    while(lo < hi)
-    {
-      unsigned long long mid = lo + (hi - lo) / 2;
-      if((unsigned long long)keys[mid] < x) { lo = mid + 1; } else { hi = mid; }
-    }
-    return lo - run_offsets[k];
-  };
-  unsigned long long x = 0;
-  if(r == ranges) { x = n_a + 1; }
-  else if(r > 0)
-  {
-    unsigned long long target = r * step, lo = 0, hi = n_a + 1;
-    while(lo < hi)
-    {
-      unsigned long long mid = lo + (hi - lo) / 2, placed = mid;
-      for(int k = 0; k < S; k++) { placed += below(mid, k); }
-      if(placed < target) { lo = mid + 1; } else { hi = mid; }
-    }
-    x = lo;
-  }
-  splitters[r] = x;
-  for(int k = 0; k < S; k++) { bounds[r * S + k] = below(x, k); }
-}
-
-// Merges the sorted pieces [offsets[k], offsets[k + 1]) of `src` pairwise, ping-ponging between two buffers.
-template<class KeyT>
-static int merge_pieces(KeyT* src, KeyT* dst, std::vector<uint64_t> offsets, cudaStream_t stream, DeviceBuffer& temp, KeyT** result)
-{
-  while(offsets.size() > 2)
-  {
-    std::vector<uint64_t> next; next.push_back(0);
-    for(size_t k = 0; k + 1 < offsets.size(); k += 2)
-    {
-      uint64_t begin = offsets[k], middle = offsets[k + 1], end = (k + 2 < offsets.size() ? offsets[k + 2] : offsets[k + 1]);
-      if(end == middle || middle == begin)
-      {
-        if(end > begin) { BWTM_CUDA(cudaMemcpyAsync(dst + begin, src + begin, (end - begin) * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream)); }
-      }
-      else
-      {
-        size_t bytes = 0;
-        BWTM_CUDA(cub::DeviceMerge::MergeKeys(nullptr, bytes, src + begin, (int)(middle - begin), src + middle, (int)(end - middle), dst + begin, ::cuda::std::less<>{}, stream));
-        if(bytes > temp.bytes) { BWTM_CUDA(cudaStreamSynchronize(stream)); BWTM_TRY(temp.allocate(bytes)); }
-        BWTM_CUDA(cub::DeviceMerge::MergeKeys(temp.ptr, bytes, src + begin, (int)(middle - begin), src + middle, (int)(end - middle), dst + begin, ::cuda::std::less<>{}, stream));
-        count_launch(2);
-      }
-      next.push_back(end);
-    }
-    offsets.swap(next);
-    std::swap(src, dst);
-  }
-  *result = src;
-  return BWTM_OK;
-}
-
 // Memory the pool could hand out right now: free device memory plus what the pool holds but does not use.
 // cudaMemGetInfo costs milliseconds: only called when the answer can matter (see choose_batches).
 static uint64_t available_device_bytes()
@@ -1438,37 +1372,7 @@ static int merge_in_batches(bwtm_index* a, bwtm_index* b, const bwtm_merge_optio
     return BWTM_ERR_INTERNAL;
   }
 
-  // 2. ranges of A positions holding about `step` merged positions each, and where they cut the runs
-  timer.start();
-  const uint64_t total = n_a + n_b;
-  const uint64_t step = clamp_slab(options->slab_symbols, total);
-  const uint64_t ranges = std::max<uint64_t>(1, div_up(total, step));
-  DeviceBuffer d_offsets, d_splitters, d_bounds;
-  BWTM_TRY(d_offsets.allocate((S + 1) * sizeof(unsigned long long)));
-  BWTM_TRY(d_splitters.allocate((ranges + 1) * sizeof(unsigned long long)));
-  BWTM_TRY(d_bounds.allocate((ranges + 1) * S * sizeof(unsigned long long)));
-  BWTM_CUDA(cudaMemcpyAsync(d_offsets.ptr, run_offsets.data(), (S + 1) * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
-  batch_splitters<KeyT><<<(unsigned)div_up(ranges + 1, 64), 64, 0, stream>>>(runs.as<KeyT>(), d_offsets.as<unsigned long long>(), S, n_a, step, ranges,
-                                                                             d_splitters.as<unsigned long long>(), d_bounds.as<unsigned long long>());
-  BWTM_LAUNCH_CHECK();
-  std::vector<unsigned long long> splitters(ranges + 1), bounds((ranges + 1) * S);
-  BWTM_CUDA(cudaMemcpyAsync(splitters.data(), d_splitters.ptr, (ranges + 1) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaMemcpyAsync(bounds.data(), d_bounds.ptr, (ranges + 1) * S * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-  BWTM_CUDA(cudaStreamSynchronize(stream));
-  uint64_t largest = 0;
-  std::vector<uint64_t> keys_before(ranges + 1, 0);
-  for(uint64_t r = 0; r <= ranges; r++)
-  {
-    for(int k = 0; k < S; k++) { keys_before[r] += bounds[r * S + k]; }
-    if(r > 0) { largest = std::max(largest, keys_before[r] - keys_before[r - 1]); }
-  }
-  DeviceBuffer gathered, merged_keys, merge_temp;
-  BWTM_TRY(gathered.allocate(std::max<uint64_t>(largest, 1) * sizeof(KeyT)));
-  BWTM_TRY(merged_keys.allocate(std::max<uint64_t>(largest, 1) * sizeof(KeyT)));
-  sort_ms = timer.stop();
-  timings->sort_seconds += sort_ms * 1e-3;
-
-  // 3. range by range: gather + merge the pieces, interleave, encode
+  // 2. + 3. ranges of A positions, the pieces of the runs in each gathered, merged, interleaved and encoded
   DeviceBuffer distinct; BWTM_TRY(distinct.allocate(sizeof(unsigned long long)));
   BWTM_CUDA(cudaMemsetAsync(distinct.ptr, 0, sizeof(unsigned long long), stream));
   DeviceBuffer control; BWTM_TRY(control.allocate(sizeof(EncodeControl)));
@@ -1476,37 +1380,15 @@ static int merge_in_batches(bwtm_index* a, bwtm_index* b, const bwtm_merge_optio
   OutputBuffer out = { nullptr, 0, 0, nullptr };
   int rc = ensure_capacity(&out, a->rle_bytes + b->rle_bytes + ((a->rle_bytes + b->rle_bytes) >> 2) + (1 << 20), 0, stream);
   float interleave_ms = 0.0f, encode_ms = 0.0f, merge_ms = 0.0f;
-  for(uint64_t r = 0; rc == BWTM_OK && r < ranges; r++)
+  if(rc == BWTM_OK)
   {
-    const uint64_t count = keys_before[r + 1] - keys_before[r];
-    const uint64_t begin = splitters[r] + keys_before[r];
-    const uint64_t end = (r + 1 == ranges ? total : splitters[r + 1] + keys_before[r + 1]);
-    const bool last = (r + 1 == ranges);
-    if(end == begin && !last) { continue; }
-    KeyT* range_keys = gathered.as<KeyT>();
-    timer.start();
-    std::vector<uint64_t> piece_offsets(1, 0);
-    for(int k = 0; rc == BWTM_OK && k < S; k++)
-    {
-      uint64_t from = run_offsets[k] + bounds[r * S + k], piece = bounds[(r + 1) * S + k] - bounds[r * S + k];
-      if(piece > 0 && cudaMemcpyAsync(gathered.as<KeyT>() + piece_offsets.back(), runs.as<KeyT>() + from, piece * sizeof(KeyT), cudaMemcpyDeviceToDevice, stream) != cudaSuccess)
-      {
-        rc = cuda_failed(cudaGetLastError(), "gather of a run piece", __FILE__, __LINE__);
-      }
-      piece_offsets.push_back(piece_offsets.back() + piece);
-    }
-    if(rc == BWTM_OK) { rc = merge_pieces<KeyT>(gathered.as<KeyT>(), merged_keys.as<KeyT>(), piece_offsets, stream, merge_temp, &range_keys); }
-    merge_ms += timer.stop();
-    if(rc == BWTM_OK)
-    {
-      rc = interleave_range<KeyT>(a, b, range_keys, keys_before[r], count, begin, end, options->slab_symbols, &out, control.as<EncodeControl>(),
-                                  last, &interleave_ms, &encode_ms, stream, distinct.as<unsigned long long>(), nullptr);
-    }
+    rc = merge_ranges<KeyT>(a, b, runs.as<KeyT>(), run_offsets, 0, n_a + 1, 0, 0, n_a + n_b, options, &out, control.as<EncodeControl>(), true,
+                            &merge_ms, &interleave_ms, &encode_ms, distinct.as<unsigned long long>(), stream);
   }
   if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
   timings->sort_seconds += merge_ms * 1e-3;
   timings->interleave_seconds = interleave_ms * 1e-3; timings->encode_seconds = encode_ms * 1e-3;
-  runs.release(); gathered.release(); merged_keys.release();
+  runs.release();
 
   EncodeControl ctl;
   BWTM_CUDA(cudaMemcpy(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost));

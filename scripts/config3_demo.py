@@ -43,6 +43,7 @@ def main():
     ap.add_argument("--steps", type=int, default=2)
     ap.add_argument("--patterns", type=int, default=100_000)
     ap.add_argument("--no-verify", action="store_true")
+    ap.add_argument("--sequence-blocks", type=int, default=0, help="search batches (needed where two full key buffers do not fit: 2 GPUs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local); bwtm_b200.set_device(local)
@@ -66,7 +67,7 @@ def main():
         pats = [p for p in synth.patterns(synth.genome(50_000_000, 42), args.patterns, 32, 99)]
     pre = A.count(pats) + B.count(pats)
 
-    params = MergeParameters()
+    params = MergeParameters(); params.sequence_blocks = args.sequence_blocks
     times = []
     M = None
     for step in range(args.steps + 1):

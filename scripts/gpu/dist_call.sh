@@ -13,3 +13,6 @@ BWTM_DEBUG=1 BWTM_BENCH_NO_DIST_E2E=1 timeout 600 $RUN --master-port 29535 bench
 if [ "${SKIP_C5:-0}" != "1" ]; then
 timeout 1500 $RUN --master-port 29536 bench.py --gpus $N --config 5 --steps 5 --warmup 2 > gpurun_out/r02_bench_c5_n$N.json 2> gpurun_out/r02_bench_c5_n$N.err; echo "bench c5 rc=$?"; tail -c 1800 gpurun_out/r02_bench_c5_n$N.json; echo; tail -3 gpurun_out/r02_bench_c5_n$N.err
 fi
+if [ "${RUN_C3:-0}" == "1" ]; then
+timeout 1500 $RUN --master-port 29537 scripts/config3_demo.py --steps ${C3_STEPS:-2} > gpurun_out/r02_config3_n$N.txt 2> gpurun_out/r02_config3_n$N.err; echo "config3 rc=$?"; grep -v "^\*\|OMP" gpurun_out/r02_config3_n$N.txt | tail -16 | cut -c1-400; grep -v "^\*\|OMP\|Warning" gpurun_out/r02_config3_n$N.err | tail -5
+fi

@@ -31,10 +31,13 @@ def main():
             comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
         check_cases(comm, rank, thr, todo)
     os.environ.pop("BWTM_NCCL_EXCHANGE", None)
+    dist.barrier(); comm.close(); comm = bwtm_b200.Communicator.from_torch(dist, rank, world)
+    check_cases(comm, rank, thr, cases[:4], sequence_blocks=3)      # the search in batches, pieces merged range by range
+    check_cases(comm, rank, thr, cases[3:], sequence_blocks=7)
     check_failures(comm, rank, world, thr)
     dist.barrier()
     if rank == 0:
-        print("dist_check ok: %d ranks, %d cases" % (world, sum(len(todo) for _, todo in runs)))
+        print("dist_check ok: %d ranks, %d cases (+ batched search, + injected failures)" % (world, sum(len(todo) for _, todo in runs)))
     comm.close()
     dist.destroy_process_group()
 
@@ -57,10 +60,10 @@ def check_failures(comm, rank, world, thr):
             assert np.array_equal(comm.merge(A, B, keep_inputs=True).rle(), want), "rank %d: merge after a failed merge differs" % rank
 
 
-def check_cases(comm, rank, thr, cases):
+def check_cases(comm, rank, thr, cases, sequence_blocks=1):
     for G, n, L, slab in cases:
         A = FMI.synthetic(G, 42, L, thr, [(1, n)]); B = FMI.synthetic(G, 42, L, thr, [(2, max(1, n // 2))])
-        p = MergeParameters(); p.slab_symbols = slab
+        p = MergeParameters(); p.slab_symbols = slab; p.sequence_blocks = sequence_blocks
         single = FMI.merge(A, B, p, keep_inputs=True)
         multi = comm.merge(A, B, p, keep_inputs=True)
         want = single.rle()
