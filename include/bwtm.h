@@ -224,8 +224,14 @@ int bwtm_shard_range(uint64_t total, uint32_t rank, uint32_t world, uint64_t* fi
 int bwtm_comm_unique_id(uint8_t id[BWTM_COMM_ID_BYTES]);               /* rank 0; broadcast it by any means */
 int bwtm_comm_create(const uint8_t id[BWTM_COMM_ID_BYTES], int rank, int world, bwtm_comm** out);
 int bwtm_comm_destroy(bwtm_comm* comm);
-/* Collective: every rank calls it with its replicas of a and b. On return every rank holds the
-   complete merged index (RLE bytes all-gathered, rank structure rebuilt locally). */
+/* Collective: every rank calls it with its replicas of a and b. On return every rank holds the complete merged index:
+   the run-length bytes of all slices gathered, the rank structure built from the plane chunks the ranks store into each
+   other's record windows (or decoded from the bytes when peer windows are not available).
+   It fails together: if one rank fails locally (allocation, capacity, invalid input), every rank returns an error from
+   the same call and the communicator stays usable.
+   options->sequence_blocks > 1 (the same value on every rank): the ranks search their share of b in that many batches,
+   keep them as sorted runs, exchange the runs piece by piece and merge them range by range while interleaving -- for
+   inputs whose rank-array values do not fit twice into a GPU. 0 and 1: one batch (no automatic choice here). */
 int bwtm_merge_distributed(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
                            const bwtm_merge_options* options, bwtm_index** out, bwtm_timings* timings);
 
