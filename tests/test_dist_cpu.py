@@ -80,3 +80,48 @@ def test_shard_range_matches_reference_blocks():
             blocks = [bwtm_b200.shard_range(total, r, world) for r in range(world)]
             assert sum(c for _, c in blocks) == total
             assert all(f == (total * r) // world for r, (f, _) in enumerate(blocks))
+
+
+def _model_worker(rank, world, port, batches, queue):
+    import sys
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        here = os.path.dirname(os.path.abspath(__file__)); root = os.path.dirname(here)
+        for p in (root, os.path.join(root, "bwt-merge_b200"), here):
+            if p not in sys.path:
+                sys.path.insert(0, p)
+        from oracle.oracle import Oracle
+        from conftest import make_collection
+        from dist_model import distributed_merge_model
+        orc = Oracle()
+        _, bwt_a = make_collection(orc, 3000, 260, 45, 0.02, 42, 1, 0.01)
+        _, bwt_b = make_collection(orc, 3000, 150, 45, 0.02, 42, 2, 0.01)
+        A, B = orc.from_comps(bwt_a), orc.from_comps(bwt_b)
+        begin, end, symbols = distributed_merge_model(orc, A, B, batches)
+        want = orc.merge(A, B).decode()
+        queue.put((rank, begin, end, bool(np.array_equal(symbols, want[begin:end])), len(want)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,batches", [(2, 1), (2, 3), (3, 2)])
+def test_protocol_of_the_distributed_merge_on_gloo(world, batches):
+    """tests/dist_model.py restates the protocol of bwtm_merge_distributed (shards, splitter rule, piece layout of the
+    one-shot and the batched exchange, slice boundaries) over gloo with the oracle doing the per-rank work: the slices of
+    the ranks must tile the merged BWT of the oracle exactly."""
+    ctx = mp.get_context("spawn")
+    queue = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_model_worker, args=(r, world, port, batches, queue)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted(queue.get(timeout=240) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    position = 0
+    for rank, begin, end, same, total in results:
+        assert begin == position and same, (rank, begin, end, same)
+        position = end
+    assert position == results[0][4]
