@@ -420,6 +420,7 @@ def main():
     sampler = ClockSampler(local_rank)
     barrier()
     sampler.start()
+    time.sleep(0.25)      # nvidia-smi needs a moment before its first sample; the timed region can be shorter than that
     launches0 = bwtm_b200.kernel_launches()
     stage = {k: 0.0 for k in ("search", "sort", "exchange", "interleave", "encode", "index", "pair_index")}
     last = None
