@@ -1,4 +1,5 @@
-// K1: the rank-array search, and K2: its radix sort.
+// K1: the rank-array search (single-step form), and K2: the sort of its values (MSD partition of the high key
+// bits + counting of the low bits; the library's radix sort for small inputs).
 //
 // Replaces buildRA (fmi.cpp:272-334).  The reference walks the reverse trie of B depth first and
 // emits (rank in A, number of suffixes) per trie node; 87-96 % of its nodes are singletons
