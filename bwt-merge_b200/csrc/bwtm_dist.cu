@@ -704,7 +704,12 @@ static int merge_distributed_impl(bwtm_comm* comm, bwtm_index* a, bwtm_index* b,
   }
   if(parallel) { encode_ms += timer.stop(); } else { timer.stop(); }
   rc = agree_on_status(comm, rc, stream, "chained writer");
-  if(rc != BWTM_OK) { device_free(out.ptr); return rc; }
+  if(rc != BWTM_OK)
+  {
+    if(shipping) { cudaStreamSynchronize(comm->ship_stream); }   // the plane chunks are freed on return: nobody may still read them
+    device_free(out.ptr);
+    return rc;
+  }
   BWTM_CUDA(cudaMemcpyAsync(&ctl, control.ptr, sizeof(EncodeControl), cudaMemcpyDeviceToHost, stream));
   BWTM_CUDA(cudaStreamSynchronize(stream));
   timings->interleave_seconds = interleave_ms * 1e-3;
